@@ -13,6 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libsplicing_ref.so")
+PORT_SO = os.path.join(HERE, "libmiso_oracle.so")
 
 _i32p = C.POINTER(C.c_int)
 _f64p = C.POINTER(C.c_double)
@@ -47,9 +48,24 @@ def _cigar_array(cigars):
     return arr
 
 
+class _Prefixed:
+    """lib.refh_xxx / lib.mo_xxx behind one attribute namespace."""
+
+    def __init__(self, lib, prefix):
+        self._lib, self._prefix = lib, prefix
+
+    def __getattr__(self, name):
+        assert name.startswith("refh_")
+        return getattr(self._lib, self._prefix + name[5:])
+
+
 class RefOracle:
-    def __init__(self, path=REF_SO):
-        self.lib = C.CDLL(path)
+    """kind == "reference": the unmodified reference C (oracle/_ref);
+    PortOracle below shares every method except the simulators."""
+    kind = "reference"
+
+    def __init__(self, path=REF_SO, prefix="refh_"):
+        self.lib = _Prefixed(C.CDLL(path), prefix)
         self.lib.refh_init()
 
     # -- setup stage ---------------------------------------------------
@@ -215,3 +231,20 @@ class RefOracle:
         if r != 0:
             raise RuntimeError("reference returned error %d" % r)
         return pos, self._unpack(buf, off, n), isoout
+
+
+class PortOracle(RefOracle):
+    """kind == "port": oracle/miso_oracle.c, the plain-C restatement."""
+    kind = "port"
+
+    def __init__(self, path=PORT_SO):
+        RefOracle.__init__(self, path, "mo_")
+
+    def simulate_se(self, *a, **k):
+        raise NotImplementedError("simulators exist only in oracle/_ref")
+
+    simulate_pe = simulate_se
+
+
+def port_available():
+    return os.path.isfile(PORT_SO)
