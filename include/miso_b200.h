@@ -1,0 +1,218 @@
+/*
+ * include/miso_b200.h -- C ABI of libmiso_b200.so
+ *
+ * B200-native drop-in for the reference's per-gene MCMC PSI sampler, i.e. the
+ * C entry points that pysplicing's extension module binds
+ * (/root/reference/pysplicing/src/pysplicing.c:41-131 `MISO`, :152-244
+ * `MISOPaired`, :246-278 `createGene`) and that are declared in
+ * /root/reference/pysplicing/include/splicing.h:203-238
+ * (`splicing_miso`, `splicing_miso_paired`), re-cut for a GPU: many genes per
+ * call, flat pointer + size arguments, caller-owned output buffers.
+ *
+ * Plain C only: no C++ and no framework types cross this boundary.  Every
+ * function returns 0 on success or one of the MISOB200_E* codes (the values
+ * follow /root/reference/pysplicing/include/splicing_error.h:316-366 where a
+ * counterpart exists); misob200_last_error() gives the message.
+ *
+ * Pipeline
+ *   misob200_plan_create        empty plan (opaque, host side)
+ *   misob200_plan_append        reads + gene structures  ->  compatibility
+ *                               codes, draw order, read classes, packed tiles
+ *                               (replaces splicing_matchIso[_paired],
+ *                               splicing_order_matches, splicing_i_miso_classes
+ *                               and the effective-length block:
+ *                               src/solve.c:8-218, src/miso.c:758-784,
+ *                               src/miso_paired.c:378-419)
+ *   misob200_run                H2D tiles, sm_100a chain kernel (one warp per
+ *                               gene-chain, whole burn-in + sampling loop on
+ *                               chip), D2H posteriors (replaces the loop of
+ *                               src/miso.c:827-947 / src/miso_paired.c:431-538)
+ *   misob200_summarize          posterior mean + 95% CI per gene on the device
+ *                               (misopy/credible_intervals.py:31-55)
+ */
+#ifndef MISO_B200_H
+#define MISO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (splicing_error.h values where they exist) ---------- */
+#define MISOB200_SUCCESS        0
+#define MISOB200_FAILURE        1
+#define MISOB200_ENOMEM         2
+#define MISOB200_EINVAL         4
+#define MISOB200_UNIMPLEMENTED 12
+#define MISOB200_ECUDA        100	/* CUDA runtime / no device */
+#define MISOB200_ENCCL        101
+
+/* ---- enums: pysplicing/pysplicing/__init__.py:2-13 ------------------- */
+#define MISOB200_START_AUTO      0
+#define MISOB200_START_UNIFORM   1
+#define MISOB200_STOP_FIXEDNO    0
+#define MISOB200_ALGO_REASSIGN   0
+
+#define MISOB200_MAX_ISO         8	/* isoforms per gene handled on chip */
+
+/* ---- input: a batch of genes with their reads ------------------------- */
+/*
+ * Gene structure is what createGene receives (pysplicing.c:246-278) after
+ * splicing_create_gene / splicing_gff_exon_start_end have expanded it
+ * (src/simulator.c:9-66, src/gff.c:728-779): for every isoform the list of
+ * its exons as 1-based inclusive [start,end], in isoform order.
+ * Reads are what MISO / MISOPaired receive: 1-based start positions and
+ * CIGAR strings (pysplicing.c:62,173); for paired-end the two mates of a
+ * pair are consecutive (src/solve.c:139).
+ */
+typedef struct misob200_reads {
+  int32_t n_genes;
+  const int32_t *iso_off;	/* [n_genes+1]  first isoform of each gene      */
+  const int32_t *exon_off;	/* [n_iso+1]    first exon of each isoform       */
+  const int32_t *exon_start;	/* [n_exon]                                      */
+  const int32_t *exon_end;	/* [n_exon]                                      */
+  const int64_t *read_off;	/* [n_genes+1]  first read (SE) / mate (PE)      */
+  const int32_t *position;	/* [n_reads]    1-based                          */
+  const int64_t *cigar_off;	/* [n_reads+1]  byte offsets into cigar          */
+  const char *cigar;		/* NUL-terminated strings, back to back          */
+  const double *hyper;		/* [n_iso] Dirichlet prior, or NULL for all 1.0  */
+  const uint32_t *gene_id;	/* [n_genes] RNG stream ids, or NULL for 0..n-1  */
+  int32_t read_len;
+  int32_t overhang;		/* 0 means 1, as src/miso.c:690                  */
+  int32_t paired;		/* 0: MISO, 1: MISOPaired                        */
+  double frag_mean, frag_var, num_devs;	/* paired only (pysplicing.c:173) */
+} misob200_reads_t;
+
+typedef struct misob200_plan misob200_plan_t;	/* opaque */
+
+/* ---- run parameters: positional tail of MISO(...) --------------------- */
+typedef struct misob200_params {
+  int32_t n_iters;		/* noIterations, default 5000 */
+  int32_t burn_in;		/* noBurnIn,     default 500  */
+  int32_t lag;			/* noLag,        default 10   */
+  int32_t n_chains;		/* no_chains,    default 6    */
+  int32_t start;		/* MISOB200_START_*           */
+  int32_t stop;			/* MISOB200_STOP_FIXEDNO only */
+  int32_t algo;			/* MISOB200_ALGO_REASSIGN only */
+  int32_t device;		/* CUDA ordinal               */
+  uint64_t seed;		/* stream = Philox4x32-10 keyed (seed; gene_id, chain) */
+} misob200_params_t;
+
+/* per-gene layout of the outputs of misob200_run (all caller-owned):
+ *   samples   : for gene g, K_g x (n_chains*S) doubles, column-major, column
+ *               s*n_chains + c = sample s of chain c (src/miso.c:884-888),
+ *               S = (n_iters-burn_in)/lag; genes back to back at
+ *               misob200_plan_sample_offset(plan, g, ...)
+ *   loglik    : n_chains*S doubles per gene, same column order
+ *   assignment: one int32 per read (SE) / pair (PE) in input order, chain 0,
+ *               -1 = incompatible (src/miso.c:943-946)
+ *   rundata   : 9 int32 per gene, the fields of splicing_miso_rundata_t
+ *               (include/splicing.h:143-146) in declaration order
+ *   status    : 1 int32 per gene, 0 ok, else MISOB200_E*
+ */
+
+int misob200_version(void);
+const char *misob200_last_error(void);
+
+/* device bring-up; fails loudly (MISOB200_ECUDA) if no sm_100 device */
+int misob200_init(int device);
+int misob200_shutdown(void);
+int misob200_device_count(int *count);
+
+int misob200_plan_create(misob200_plan_t **plan);
+int misob200_plan_destroy(misob200_plan_t *plan);
+int misob200_plan_append(misob200_plan_t *plan, const misob200_reads_t *reads,
+			 int n_threads);
+
+/* keep the code matrix and draw order of later appends for
+   misob200_plan_gene_match (parity tests; costs 4 bytes per read x isoform) */
+int misob200_plan_keep_match(misob200_plan_t *plan, int on);
+
+int misob200_plan_size(const misob200_plan_t *plan, int32_t *n_genes,
+		       int64_t *n_reads, int64_t *tile_bytes);
+/* per gene: K, number of reads/pairs R, reads that draw each pass R2,
+   number of read classes, per-gene status from the setup stage */
+int misob200_plan_gene_info(const misob200_plan_t *plan, int32_t gene,
+			    int32_t *n_iso, int32_t *n_reads, int32_t *n_drawn,
+			    int32_t *n_classes, int32_t *status);
+/* class_templates: n_classes x K doubles, row per class (this is the
+   transposed form pysplicing returns, pysplicing.c:120-121); counts likewise.
+   SE: exact columns (miso_paired.c:576-619); PE: zero/non-zero patterns
+   (miso_paired.c:628-681) */
+int misob200_plan_gene_classes(const misob200_plan_t *plan, int32_t gene,
+			       double *class_templates, double *class_counts);
+/* the setup-stage products, for parity tests: code matrix K x R column-major
+   (0 = incompatible, SE 1, PE fragment - fragment_start + 1) and draw order */
+int misob200_plan_gene_match(const misob200_plan_t *plan, int32_t gene,
+			     int32_t *codes, int32_t *order);
+int misob200_plan_fragment_table(const misob200_plan_t *plan, int32_t cap,
+				 double *prob, int32_t *frag_start,
+				 int32_t *n_len);
+/* offsets (in elements) of gene g inside samples / loglik / assignment */
+int misob200_plan_offsets(const misob200_plan_t *plan,
+			  const misob200_params_t *params, int32_t gene,
+			  int64_t *sample_off, int64_t *loglik_off,
+			  int64_t *assign_off);
+int misob200_plan_output_sizes(const misob200_plan_t *plan,
+			       const misob200_params_t *params,
+			       int64_t *n_samples_f64, int64_t *n_loglik_f64,
+			       int64_t *n_assign_i32);
+
+/* timing_ms (may be NULL): [0] H2D, [1] kernels, [2] D2H, [3] total, from
+   CUDA events on the run stream; launches = kernels launched (may be NULL) */
+int misob200_run(misob200_plan_t *plan, const misob200_params_t *params,
+		 double *samples, double *loglik, int32_t *assignment,
+		 int32_t *rundata, int32_t *status, double *timing_ms,
+		 int32_t *launches);
+
+/* Device-resident variant for measurement: upload once, run many times,
+   download once.  misob200_run == upload + run_resident + download. */
+int misob200_upload(misob200_plan_t *plan, const misob200_params_t *params);
+int misob200_run_resident(misob200_plan_t *plan, double *kernel_ms,
+			  int32_t *launches);
+int misob200_download(misob200_plan_t *plan, double *samples, double *loglik,
+		      int32_t *assignment, int32_t *rundata, int32_t *status);
+int misob200_release_device(misob200_plan_t *plan);
+
+/* Posterior summaries on the device (needs a resident run): per gene a
+   256-byte record {mean[8], ci_low[8], ci_high[8] (f64); assigned_counts[8],
+   n_iso, accepted, rejected, status (i32); pad}.  summary: n_genes*32 f64. */
+#define MISOB200_SUMMARY_F64 32
+int misob200_summarize(misob200_plan_t *plan, double *summary);
+
+/* ---- multi-GPU: genes are sharded by the caller, one process per GPU;
+   the only exchange is one all-gather of the summary records ------------- */
+int misob200_comm_unique_id(char *id128);		/* rank 0 */
+int misob200_comm_init(const char *id128, int n_ranks, int rank);
+int misob200_comm_allgather(const double *mine, int64_t n_f64_per_rank,
+			    double *all);
+int misob200_comm_barrier_max(double *value);	/* in: local, out: max */
+int misob200_comm_destroy(void);
+
+/* page-locked host buffers for the outputs of misob200_run / _download
+   (optional: any host pointer works, pinned ones copy at link speed) */
+void *misob200_host_alloc(int64_t bytes);
+int misob200_host_free(void *p);
+
+/* ---- synthetic workloads (BASELINE.json configs 2 and 3) -------------- */
+typedef struct misob200_workload misob200_workload_t;	/* opaque */
+/* kind 0: K=2 skipped-exon SE events (cfg-2); kind 1: K in [2,8] paired-end
+   events with a N(frag_mean, frag_var) insert model (cfg-3).  Genes get ids
+   first_gene_id .. first_gene_id+n_genes-1 and are generated from (seed, id)
+   only, so any shard of a workload can be rebuilt independently. */
+int misob200_workload_create(int kind, int32_t n_genes, int32_t reads_per_gene,
+			     int32_t read_len, double frag_mean,
+			     double frag_var, double num_devs, uint64_t seed,
+			     uint32_t first_gene_id, int n_threads,
+			     misob200_workload_t **out);
+int misob200_workload_view(const misob200_workload_t *w,
+			   misob200_reads_t *view);
+int misob200_workload_truth(const misob200_workload_t *w, int32_t gene,
+			    double *psi);
+int misob200_workload_destroy(misob200_workload_t *w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

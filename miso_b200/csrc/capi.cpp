@@ -1,0 +1,178 @@
+// miso_b200/csrc/capi.cpp -- extern "C" entry points declared in include/miso_b200.h.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "plan.hpp"
+
+namespace misob200 {
+const char *last_error();
+void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, long long *n_loglik);
+int device_init(int device);
+int upload(Plan &plan, const misob200_params_t &p);
+int run_resident(Plan &plan, double *kernel_ms, int *launches);
+int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, int32_t *rundata,
+             int32_t *status);
+int release_device(Plan &plan);
+int summarize(Plan &plan, double *summary);
+int run_timing(Plan &plan, double *timing_ms);
+int device_count(int *n);
+}  // namespace misob200
+
+using namespace misob200;
+
+struct misob200_plan { Plan p; };
+
+extern "C" {
+
+int misob200_version(void) { return 100; }
+const char *misob200_last_error(void) { return last_error(); }
+
+int misob200_init(int device) { return device_init(device); }
+int misob200_shutdown(void) { return 0; }
+int misob200_device_count(int *count) { return device_count(count); }
+
+int misob200_plan_create(misob200_plan_t **plan) {
+  if (!plan) return MISOB200_EINVAL;
+  *plan = new misob200_plan();
+  return 0;
+}
+int misob200_plan_destroy(misob200_plan_t *plan) {
+  if (!plan) return 0;
+  release_device(plan->p);
+  delete plan;
+  return 0;
+}
+int misob200_plan_keep_match(misob200_plan_t *plan, int on) {
+  if (!plan) return MISOB200_EINVAL;
+  plan->p.keep_match = on != 0;
+  return 0;
+}
+int misob200_plan_append(misob200_plan_t *plan, const misob200_reads_t *reads, int n_threads) {
+  if (!plan || !reads) { set_error("plan_append: null argument"); return MISOB200_EINVAL; }
+  if (plan->p.dev) release_device(plan->p);
+  return plan_append(plan->p, *reads, n_threads);
+}
+int misob200_plan_size(const misob200_plan_t *plan, int32_t *n_genes, int64_t *n_reads, int64_t *tile_bytes) {
+  if (!plan) return MISOB200_EINVAL;
+  if (n_genes) *n_genes = (int32_t) plan->p.desc.size();
+  if (n_reads) *n_reads = plan->p.n_reads;
+  if (tile_bytes) *tile_bytes = (int64_t) plan->p.tiles.size();
+  return 0;
+}
+static int check_gene(const misob200_plan_t *plan, int32_t gene) {
+  if (!plan || gene < 0 || (size_t) gene >= plan->p.host.size()) {
+    set_error("gene index out of range");
+    return MISOB200_EINVAL;
+  }
+  return 0;
+}
+int misob200_plan_gene_info(const misob200_plan_t *plan, int32_t gene, int32_t *n_iso, int32_t *n_reads,
+                            int32_t *n_drawn, int32_t *n_classes, int32_t *status) {
+  if (int rc = check_gene(plan, gene)) return rc;
+  const GeneHost &h = plan->p.host[gene];
+  if (n_iso) *n_iso = h.K;
+  if (n_reads) *n_reads = h.R;
+  if (n_drawn) *n_drawn = h.R2;
+  if (n_classes) *n_classes = h.ncls;
+  if (status) *status = h.status;
+  return 0;
+}
+int misob200_plan_gene_classes(const misob200_plan_t *plan, int32_t gene, double *class_templates,
+                               double *class_counts) {
+  if (int rc = check_gene(plan, gene)) return rc;
+  const GeneHost &h = plan->p.host[gene];
+  if (class_templates && !h.class_templates.empty())
+    std::memcpy(class_templates, h.class_templates.data(), h.class_templates.size() * sizeof(double));
+  if (class_counts && !h.class_counts.empty())
+    std::memcpy(class_counts, h.class_counts.data(), h.class_counts.size() * sizeof(double));
+  return 0;
+}
+int misob200_plan_gene_match(const misob200_plan_t *plan, int32_t gene, int32_t *codes, int32_t *order) {
+  if (int rc = check_gene(plan, gene)) return rc;
+  const GeneHost &h = plan->p.host[gene];
+  if (h.status == 0 && h.R > 0 && h.codes.empty()) {
+    set_error("plan was built without keep_match");
+    return MISOB200_EINVAL;
+  }
+  if (codes && !h.codes.empty()) std::memcpy(codes, h.codes.data(), (size_t) h.K * h.R * sizeof(int32_t));
+  if (order && !h.order.empty()) std::memcpy(order, h.order.data(), (size_t) h.R * sizeof(int32_t));
+  return 0;
+}
+int misob200_plan_fragment_table(const misob200_plan_t *plan, int32_t cap, double *prob, int32_t *frag_start,
+                                 int32_t *n_len) {
+  if (!plan) return MISOB200_EINVAL;
+  const Plan &p = plan->p;
+  if (n_len) *n_len = p.frag_len_n;
+  if (frag_start) *frag_start = p.frag_start;
+  if (prob) {
+    if (cap < p.frag_len_n) { set_error("fragment table: buffer too small"); return MISOB200_EINVAL; }
+    for (int j = 0; j < p.frag_len_n; j++) prob[j] = p.ptab[j + 1];
+  }
+  return 0;
+}
+int misob200_plan_offsets(const misob200_plan_t *plan, const misob200_params_t *params, int32_t gene,
+                          int64_t *sample_off, int64_t *loglik_off, int64_t *assign_off) {
+  if (int rc = check_gene(plan, gene)) return rc;
+  if (!params || params->lag < 1) return MISOB200_EINVAL;
+  const Plan &p = plan->p;
+  const long long S = (params->n_iters - params->burn_in) / params->lag;
+  long long so = 0, lo = 0;
+  for (int g = 0; g < gene; g++) {
+    so += (long long) p.desc[g].K * params->n_chains * S;
+    lo += (long long) params->n_chains * S;
+  }
+  if (sample_off) *sample_off = so;
+  if (loglik_off) *loglik_off = lo;
+  if (assign_off) *assign_off = p.host[gene].read_base;
+  return 0;
+}
+int misob200_plan_output_sizes(const misob200_plan_t *plan, const misob200_params_t *params,
+                               int64_t *n_samples_f64, int64_t *n_loglik_f64, int64_t *n_assign_i32) {
+  if (!plan || !params || params->lag < 1) return MISOB200_EINVAL;
+  const Plan &p = plan->p;
+  const long long S = (params->n_iters - params->burn_in) / params->lag;
+  long long so = 0, lo = 0;
+  for (size_t g = 0; g < p.desc.size(); g++) {
+    so += (long long) p.desc[g].K * params->n_chains * S;
+    lo += (long long) params->n_chains * S;
+  }
+  if (n_samples_f64) *n_samples_f64 = so;
+  if (n_loglik_f64) *n_loglik_f64 = lo;
+  if (n_assign_i32) *n_assign_i32 = p.n_reads;
+  return 0;
+}
+
+int misob200_upload(misob200_plan_t *plan, const misob200_params_t *params) {
+  if (!plan || !params) { set_error("upload: null argument"); return MISOB200_EINVAL; }
+  return upload(plan->p, *params);
+}
+int misob200_run_resident(misob200_plan_t *plan, double *kernel_ms, int32_t *launches) {
+  if (!plan) return MISOB200_EINVAL;
+  return run_resident(plan->p, kernel_ms, launches);
+}
+int misob200_download(misob200_plan_t *plan, double *samples, double *loglik, int32_t *assignment,
+                      int32_t *rundata, int32_t *status) {
+  if (!plan) return MISOB200_EINVAL;
+  return download(plan->p, samples, loglik, assignment, rundata, status);
+}
+int misob200_release_device(misob200_plan_t *plan) {
+  if (!plan) return MISOB200_EINVAL;
+  return release_device(plan->p);
+}
+int misob200_run(misob200_plan_t *plan, const misob200_params_t *params, double *samples, double *loglik,
+                 int32_t *assignment, int32_t *rundata, int32_t *status, double *timing_ms,
+                 int32_t *launches) {
+  if (!plan || !params) { set_error("run: null argument"); return MISOB200_EINVAL; }
+  if (int rc = upload(plan->p, *params)) return rc;
+  if (int rc = run_resident(plan->p, nullptr, launches)) return rc;
+  if (int rc = download(plan->p, samples, loglik, assignment, rundata, status)) return rc;
+  run_timing(plan->p, timing_ms);
+  return 0;
+}
+int misob200_summarize(misob200_plan_t *plan, double *summary) {
+  if (!plan || !summary) return MISOB200_EINVAL;
+  return summarize(plan->p, summary);
+}
+
+}  // extern "C"

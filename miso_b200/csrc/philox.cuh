@@ -1,0 +1,64 @@
+// miso_b200/csrc/philox.cuh -- the random stream of the product ("miso-b200 stream v1").
+//
+// The reference draws from whatever RNG sits behind its vtable
+// (/root/reference/pysplicing/include/splicing_random.h:23-36,96-103) and never
+// seeds it; this framework defines the stream instead:
+//   Philox4x32-10, key = seed, counter = (block, tag, gene_id, chain)
+//   uniform n : word n&3 of block n>>2, tag 0   ->  (w + 0.5) * 2^-32
+//   normal  n : block n, tag 1  ->  Box-Muller on two 53-bit uniforms
+// A gene-chain consumes uniforms and normals in the order the reference's loop
+// would, so the unmodified reference driven by the same
+// stream through its vtable makes the same decisions.
+#pragma once
+#include <cstdint>
+
+namespace misob200 {
+
+#define MISOB200_PHILOX_M0 0xD2511F53u
+#define MISOB200_PHILOX_M1 0xCD9E8D57u
+#define MISOB200_PHILOX_W0 0x9E3779B9u
+#define MISOB200_PHILOX_W1 0xBB67AE85u
+
+struct PhiloxKey { uint32_t k0, k1; };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(MISOB200_PHILOX_M0, c0), lo0 = MISOB200_PHILOX_M0 * c0;
+    const uint32_t hi1 = __umulhi(MISOB200_PHILOX_M1, c2), lo1 = MISOB200_PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += MISOB200_PHILOX_W0; k1 += MISOB200_PHILOX_W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// (w + 0.5) * 2^-32, exact in fp64
+__device__ __forceinline__ double uniform_from_word(uint32_t w) {
+  return (double) w * 0x1p-32 + 0x1p-33;
+}
+
+__device__ __forceinline__ double stream_uniform(unsigned long long n, uint32_t gene, uint32_t chain,
+                                                 PhiloxKey key) {
+  uint32_t x[4];
+  philox4x32_10((uint32_t) (n >> 2), 0u, gene, chain, key.k0, key.k1, x);
+  const uint32_t sel = (uint32_t) n & 3u;
+  const uint32_t w = sel == 0 ? x[0] : sel == 1 ? x[1] : sel == 2 ? x[2] : x[3];
+  return uniform_from_word(w);
+}
+
+__device__ __forceinline__ double stream_normal(uint32_t n, uint32_t gene, uint32_t chain,
+                                                PhiloxKey key) {
+  uint32_t x[4];
+  philox4x32_10(n, 1u, gene, chain, key.k0, key.k1, x);
+  const unsigned long long a = ((unsigned long long) x[0] << 21) | (x[1] >> 11);
+  const unsigned long long b = ((unsigned long long) x[2] << 21) | (x[3] >> 11);
+  const double u1 = (double) (a + 1ull) * 0x1p-53;
+  const double u2 = (double) b * 0x1p-53;
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
+#endif
+
+}  // namespace misob200

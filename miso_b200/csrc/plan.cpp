@@ -1,0 +1,425 @@
+// miso_b200/csrc/plan.cpp -- setup stage on the host (integer work), see plan.hpp.
+//
+// Design notes (this is not a translation of the reference's setup code):
+//   * the compatibility matrix is never materialised as doubles; a read x
+//     isoform cell is one small integer code: 0 incompatible, SE 1, PE
+//     fragment_length - fragment_start + 1.  The probability the reference
+//     stores in its match matrix (src/solve.c:196-197) is ptab[code].
+//   * reads that can never draw (0 or 1 compatible isoform, src/miso.c:65-68)
+//     are folded into per-isoform constants; only the R2 reads that draw are
+//     shipped, as (K+1) byte rows in draw order (row K = flags).
+//   * the draw order must reproduce the reference's unstable sort exactly
+//     (which read receives the n-th uniform of a pass depends on it), so the
+//     index sort below follows the same published algorithm, Bentley &
+//     McIlroy's "Engineering a Sort Function" (the reference runs it from
+//     src/qsort.c through include/matrix.pmt:579-589).
+#include "plan.hpp"
+
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+namespace misob200 {
+
+namespace {
+
+struct IsoView {          // one gene's isoforms
+  int K;
+  const int32_t *exon_off;   // K+1 entries, absolute
+  const int32_t *ex_start, *ex_end;
+};
+
+// ---- CIGAR ------------------------------------------------------------
+// Semantics of splicing_parse_cigar (src/solve.c:220-306): M = X S H D are
+// match-like and clipped to read_len in total, N is an intron (negative),
+// I is skipped, S/H only at the ends, anything else is an error.
+struct Cigar {
+  int n = 0, len = 0;
+  int op[64];
+};
+
+int parse_cigar(const char *s, int read_len, Cigar &out) {
+  int mode = 0;
+  out.n = 0; out.len = 0;
+  while (*s) {
+    char *end;
+    long l = strtol(s, &end, 10);
+    char c = *end;
+    const bool clip = (c == 'S' || c == 'H');
+    if (mode == 0 && !clip) mode = 1;
+    else if (mode == 1 && clip) mode = 2;
+    else if (mode == 2 && !clip) return MISOB200_EINVAL;
+    if (c == 'M' || c == '=' || c == 'X' || clip || c == 'D') {
+      if (read_len > 0 && out.len + l > read_len) l = read_len - out.len;
+      if (out.n >= 64) return MISOB200_EINVAL;
+      out.op[out.n++] = (int) l;
+      out.len += (int) l;
+    } else if (c == 'N') {
+      if (out.n >= 64) return MISOB200_EINVAL;
+      out.op[out.n++] = (int) -l;
+    } else if (c == 'I') {
+      // not on the genome: nothing to do
+    } else {
+      return MISOB200_EINVAL;   // also hit by a trailing number without a letter
+    }
+    s = end + 1;
+  }
+  return 0;
+}
+
+// 1 if the read's blocks tile isoform k's exons from pos (src/solve.c:65-95)
+inline int compatible(const IsoView &g, int k, int pos, const Cigar &cg) {
+  int ex = g.exon_off[k];
+  const int ex_hi = g.exon_off[k + 1];
+  while (ex < ex_hi && (pos < g.ex_start[ex] || g.ex_end[ex] < pos)) ex++;
+  if (ex >= ex_hi) return 0;
+  for (int c = 0; c < cg.n; c++) {
+    const int o = cg.op[c];
+    if (o > 0) {
+      if (pos + o - 1 > g.ex_end[ex]) return 0;
+      pos += o;
+    } else {
+      if (pos != g.ex_end[ex] + 1) return 0;
+      pos -= o;
+      ex++;
+      if (ex >= ex_hi || pos != g.ex_start[ex]) return 0;
+    }
+  }
+  return 1;
+}
+
+// position on the spliced isoform, 1-based, or -1 (src/gff.c:855-900,1041-1084)
+inline int iso_coordinate(const IsoView &g, int k, int pos) {
+  int before = 0;
+  for (int ex = g.exon_off[k]; ex < g.exon_off[k + 1]; ex++) {
+    if (g.ex_end[ex] < pos) { before += g.ex_end[ex] - g.ex_start[ex] + 1; continue; }
+    if (g.ex_start[ex] <= pos) return pos - g.ex_start[ex] + 1 + before;
+    return -1;
+  }
+  return -1;
+}
+
+// ---- Bentley-McIlroy index sort -----------------------------------------
+template <class Cmp>
+struct BMSort {
+  Cmp cmp;
+  static void swp(int32_t *v, long a, long b) { int32_t t = v[a]; v[a] = v[b]; v[b] = t; }
+  void insertion(int32_t *v, long n) {
+    for (long m = 1; m < n; m++)
+      for (long l = m; l > 0 && cmp(v[l - 1], v[l]) > 0; l--) swp(v, l, l - 1);
+  }
+  long med3(const int32_t *v, long a, long b, long c) {
+    if (cmp(v[a], v[b]) < 0) {
+      if (cmp(v[b], v[c]) < 0) return b;
+      return cmp(v[a], v[c]) < 0 ? c : a;
+    }
+    if (cmp(v[b], v[c]) > 0) return b;
+    return cmp(v[a], v[c]) < 0 ? a : c;
+  }
+  void sort(int32_t *v, long n) {
+    while (true) {
+      if (n < 7) { insertion(v, n); return; }
+      long mid = n / 2;
+      if (n > 7) {
+        long lo = 0, hi = n - 1;
+        if (n > 40) {
+          const long d = n / 8;
+          lo = med3(v, lo, lo + d, lo + 2 * d);
+          mid = med3(v, mid - d, mid, mid + d);
+          hi = med3(v, hi - 2 * d, hi - d, hi);
+        }
+        mid = med3(v, lo, mid, hi);
+      }
+      swp(v, 0, mid);                       // pivot parked at v[0]
+      long a = 1, b = 1, c = n - 1, d = n - 1;
+      bool moved = false;
+      while (true) {
+        int r;
+        while (b <= c && (r = cmp(v[b], v[0])) <= 0) {
+          if (r == 0) { moved = true; swp(v, a, b); a++; }
+          b++;
+        }
+        while (b <= c && (r = cmp(v[c], v[0])) >= 0) {
+          if (r == 0) { moved = true; swp(v, c, d); d--; }
+          c--;
+        }
+        if (b > c) break;
+        swp(v, b, c);
+        moved = true;
+        b++; c--;
+      }
+      if (!moved) { insertion(v, n); return; }
+      long r = a < b - a ? a : b - a;       // equal-to-pivot runs to the middle
+      for (long i = 0; i < r; i++) swp(v, i, b - r + i);
+      r = d - c < n - d - 1 ? d - c : n - d - 1;
+      for (long i = 0; i < r; i++) swp(v, b + i, n - r + i);
+      const long left = b - a, right = d - c;
+      if (left > 1) sort(v, left);
+      if (right > 1) { v += n - right; n = right; } else return;
+    }
+  }
+};
+
+struct ColCmp {           // include/matrix.pmt:546-561 on ptab[code]
+  const int32_t *codes; const double *ptab; int K;
+  int operator()(int32_t a, int32_t b) const {
+    const int32_t *x = codes + (size_t) a * K, *y = codes + (size_t) b * K;
+    for (int i = 0; i < K; i++) {
+      const double p = ptab[x[i]], q = ptab[y[i]];
+      if (p < q) return -1;
+      if (p > q) return 1;
+    }
+    return 0;
+  }
+};
+
+struct GeneOut {
+  GeneHost h;
+  GeneDesc d;
+  std::vector<uint8_t> tile;
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &out) {
+  GeneHost &h = out.h;
+  GeneDesc &d = out.d;
+  std::memset(&d, 0, sizeof(d));
+  const int iso0 = in.iso_off[g], K = in.iso_off[g + 1] - iso0;
+  const long long r0 = in.read_off[g], nr = in.read_off[g + 1] - r0;
+  const int paired = in.paired ? 1 : 0;
+  const int R = (int) (paired ? nr / 2 : nr);
+  h.K = K; h.R = R;
+  d.K = K; d.paired = paired;
+  d.gene_id = in.gene_id ? in.gene_id[g] : (unsigned) g;
+
+  int overhang = in.overhang == 0 ? 1 : in.overhang;
+  if (K < 2) { h.status = MISOB200_EINVAL; return; }
+  if (K > kMaxIso) { h.status = MISOB200_UNIMPLEMENTED; return; }
+  // src/miso.c:690-694
+  if (overhang < 1 || overhang >= in.read_len / 2) { h.status = MISOB200_EINVAL; return; }
+  const int n_codes = (int) plan.ptab.size();
+  if (n_codes > 256) { h.status = MISOB200_UNIMPLEMENTED; return; }   // byte codes only
+
+  IsoView gv{K, in.exon_off + iso0, in.exon_start, in.exon_end};
+  int isolen[kMaxIso], nex[kMaxIso];
+  for (int k = 0; k < K; k++) {
+    isolen[k] = 0; nex[k] = gv.exon_off[k + 1] - gv.exon_off[k];
+    for (int e = gv.exon_off[k]; e < gv.exon_off[k + 1]; e++)
+      isolen[k] += gv.ex_end[e] - gv.ex_start[e] + 1;
+  }
+
+  // ---- compatibility codes, K x R column-major --------------------------
+  std::vector<int32_t> codes((size_t) K * (R > 0 ? R : 1), 0);
+  Cigar cg, cg2;
+  for (int r = 0; r < R; r++) {
+    int32_t *col = codes.data() + (size_t) r * K;
+    if (!paired) {
+      const long long ri = r0 + r;
+      if (parse_cigar(in.cigar + in.cigar_off[ri], in.read_len, cg)) { h.status = MISOB200_EINVAL; return; }
+      if (cg.n == 0 || cg.len < in.read_len || cg.op[0] < overhang || cg.op[cg.n - 1] < overhang) continue;
+      for (int k = 0; k < K; k++) col[k] = compatible(gv, k, in.position[ri], cg);
+    } else {
+      const long long r1 = r0 + 2LL * r, r2 = r1 + 1;
+      if (parse_cigar(in.cigar + in.cigar_off[r1], in.read_len, cg) ||
+          parse_cigar(in.cigar + in.cigar_off[r2], in.read_len, cg2)) { h.status = MISOB200_EINVAL; return; }
+      const bool ok1 = !(cg.n == 0 || cg.len < in.read_len || cg.op[0] < overhang || cg.op[cg.n - 1] < overhang);
+      const bool ok2 = !(cg2.n == 0 || cg2.len < in.read_len || cg2.op[0] < overhang || cg2.op[cg2.n - 1] < overhang);
+      if (!ok1 || !ok2) continue;
+      const int p1 = in.position[r1], p2 = in.position[r2];
+      for (int k = 0; k < K; k++) {
+        if (!compatible(gv, k, p1, cg) || !compatible(gv, k, p2, cg2)) continue;
+        // src/solve.c:190-198
+        const int frag = iso_coordinate(gv, k, p2) - iso_coordinate(gv, k, p1) + in.read_len;
+        if (frag < plan.frag_start || frag >= plan.frag_len_n + plan.frag_start) continue;
+        col[k] = frag - plan.frag_start + 1;
+      }
+    }
+  }
+  // odd trailing mate of a paired batch is ignored, as noreads/2 does (solve.c:187)
+
+  // ---- draw order ---------------------------------------------------------
+  std::vector<int32_t> order(R);
+  for (int r = 0; r < R; r++) order[r] = r;
+  BMSort<ColCmp> sorter{ColCmp{codes.data(), plan.ptab.data(), K}};
+  sorter.sort(order.data(), R);
+
+  // ---- read classes: histogram over zero/non-zero patterns ---------------
+  // Both reference tabulations list distinct patterns in ascending
+  // lexicographic order with isoform 0 most significant
+  // (miso_paired.c:576-619 for SE where codes are 0/1, :628-681 for PE).
+  {
+    std::vector<int> hist(1 << K, 0);
+    for (int r = 0; r < R; r++) {
+      int m = 0;
+      for (int k = 0; k < K; k++) m = (m << 1) | (codes[(size_t) r * K + k] != 0);
+      hist[m]++;
+    }
+    for (int m = 0; m < (1 << K); m++) {
+      if (!hist[m]) continue;
+      for (int k = 0; k < K; k++) h.class_templates.push_back((m >> (K - 1 - k)) & 1);
+      h.class_counts.push_back(hist[m]);
+    }
+    h.ncls = (int) h.class_counts.size();
+  }
+
+  // ---- per-gene constants ---------------------------------------------------
+  d.sigma = 0.2 / K / K;                                    // SIGMA, miso.c:328
+  d.sd = (K - 1 == 1) ? d.sigma : std::sqrt(d.sigma);       // miso.c:188
+  d.covar_const = std::pow(2 * M_PI * d.sigma, -0.5 * (K - 1));   // miso.c:101
+  {
+    double asum = 0.0, lsum = 0.0;
+    for (int k = 0; k < K; k++) {
+      const double a = in.hyper ? in.hyper[iso0 + k] : 1.0;
+      asum += a; lsum += lgamma(a);
+      d.hyper_m1[k] = a - 1.0;
+    }
+    d.lg_sum = lgamma(asum); d.lg_each = lsum;              // miso.c:177-178
+  }
+  for (int k = 0; k < K; k++) {
+    if (!paired) {                                           // miso.c:777-784
+      const int l = isolen[k] - in.read_len + 1 - 2 * (nex[k] - 1) * (overhang - 1);
+      const int eff = l > 0 ? l : 0;
+      d.rs_se[k] = -std::log((double) l);
+      d.offset[k] = std::log((double) eff);
+      d.L[k] = l;
+    } else {                                                 // miso_paired.c:403-419
+      d.L[k] = isolen[k] - plan.frag_start + 1 - 2 * (nex[k] - 1) * (overhang - 1);
+      double acc = 0.0;
+      for (int j = 0; j < plan.frag_len_n; j++) {
+        const double lp = d.L[k] - j;
+        if (lp > 0) acc += lp;
+      }
+      d.offset[k] = std::log(acc);
+    }
+  }
+  auto read_score = [&](int k, int code) -> double {
+    if (!paired) return d.rs_se[k];
+    const double lp = d.L[k] - (code - 1);
+    return -std::log(lp) + plan.ptab[code];                  // miso_paired.c:411
+  };
+
+  // ---- split reads into fixed and drawn; pack the tile ------------------------
+  h.fixed_ass.assign(R, -1);
+  h.rank_read.clear();
+  std::vector<int> drawn;
+  drawn.reserve(R);
+  for (int i = 0; i < R; i++) {
+    const int r = order[i];
+    const int32_t *col = codes.data() + (size_t) r * K;
+    int nv = 0, last = -1;
+    for (int k = 0; k < K; k++) if (col[k]) { nv++; last = k; }
+    if (nv == 0) continue;
+    if (nv == 1) {
+      h.fixed_ass[r] = (int8_t) last;
+      d.n_fixed[last]++;
+      const double s = read_score(last, col[last]);
+      d.rp_fixed += s;
+      if (!std::isfinite(s)) d.rp_always = 1;
+      continue;
+    }
+    h.fixed_ass[r] = -2;
+    drawn.push_back(r);
+    for (int k = 0; k < K; k++)
+      if (col[k] && !std::isfinite(read_score(k, col[k]))) d.rp_always = 1;
+  }
+  const int R2 = (int) drawn.size();
+  h.R2 = R2; d.R2 = R2;
+  h.rank_read.assign(drawn.begin(), drawn.end());
+  // row: 3 pad bytes, R2 codes, zero fill to a whole number of 128-read warp
+  // steps plus 16 spare bytes (a lane reads words T and T+1 of its step).
+  const int row_bytes = round_up(R2 + kTilePadFront, 128) + 16;
+  d.row_bytes = row_bytes;
+  out.tile.assign((size_t) row_bytes * (K + 1), 0);
+  for (int i = 0; i < R2; i++) {
+    const int32_t *col = codes.data() + (size_t) drawn[i] * K;
+    int nv = 0;
+    for (int k = 0; k < K; k++) {
+      out.tile[(size_t) k * row_bytes + kTilePadFront + i] = (uint8_t) col[k];
+      nv += col[k] != 0;
+    }
+    out.tile[(size_t) K * row_bytes + kTilePadFront + i] = (nv == 2) ? 1 : 2;
+  }
+  if (plan.keep_match) { h.codes = std::move(codes); h.order = std::move(order); }
+}
+
+// discretised normal insert-length table, normalised
+// (src/simulator.c:198-219, src/util.c:17-32, src/miso_paired.c:303-307)
+void fragment_table(Plan &plan) {
+  const double sd = std::sqrt(plan.frag_var);
+  int fs = (int) (plan.frag_mean - sd * plan.num_devs);
+  int fe = (int) (plan.frag_mean + sd * plan.num_devs);
+  if (fs < plan.read_len) fs = plan.read_len;
+  if (fe < fs) fe = fs;
+  const int n = fe - fs + 1;
+  std::vector<double> p(n);
+  double sum = 0.0;
+  for (int i = fs, j = 0; i <= fe; i++, j++) {
+    const double x = (i - plan.frag_mean) / sd;
+    p[j] = 0.398942280401432677939946059934 * std::exp(-0.5 * x * x) / sd;
+  }
+  for (int j = 0; j < n; j++) sum += p[j];
+  const double by = 1.0 / sum;
+  plan.ptab.assign(n + 1, 0.0);
+  for (int j = 0; j < n; j++) plan.ptab[j + 1] = p[j] * by;
+  plan.frag_start = fs; plan.frag_len_n = n;
+}
+
+}  // namespace
+
+int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads) {
+  if (in.n_genes < 0 || !in.iso_off || !in.exon_off || !in.read_off) {
+    set_error("plan_append: null or negative input"); return MISOB200_EINVAL;
+  }
+  const int paired = in.paired ? 1 : 0;
+  if (plan.paired < 0) {
+    plan.paired = paired; plan.read_len = in.read_len; plan.overhang = in.overhang;
+    plan.frag_mean = in.frag_mean; plan.frag_var = in.frag_var; plan.num_devs = in.num_devs;
+    if (paired) {
+      if (!(in.frag_var > 0)) { set_error("plan_append: frag_var must be positive"); return MISOB200_EINVAL; }
+      fragment_table(plan);
+    } else {
+      plan.ptab = {0.0, 1.0}; plan.frag_start = 0; plan.frag_len_n = 1;
+    }
+  } else if (plan.paired != paired || plan.read_len != in.read_len || plan.overhang != in.overhang ||
+             (paired && (plan.frag_mean != in.frag_mean || plan.frag_var != in.frag_var ||
+                         plan.num_devs != in.num_devs))) {
+    set_error("plan_append: a plan holds one library (read length, overhang, insert model)");
+    return MISOB200_EINVAL;
+  }
+  if (in.read_len < 0) { set_error("plan_append: negative read length"); return MISOB200_EINVAL; }
+
+  const int G = in.n_genes;
+  std::vector<GeneOut> outs(G);
+  std::atomic<int> next(0);
+  int nt = n_threads > 0 ? n_threads : (int) std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > G) nt = G > 0 ? G : 1;
+  auto work = [&]() {
+    for (int g; (g = next.fetch_add(1)) < G;) build_gene(plan, in, g, outs[g]);
+  };
+  if (nt == 1) work();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+  }
+  for (int g = 0; g < G; g++) {
+    GeneOut &o = outs[g];
+    o.h.read_base = plan.n_reads;
+    o.d.status = o.h.status;
+    o.d.tile_off = plan.tiles.size();
+    o.d.drawn_off = plan.n_drawn;
+    plan.tiles.insert(plan.tiles.end(), o.tile.begin(), o.tile.end());
+    plan.n_reads += o.h.R;
+    plan.n_drawn += (o.h.R2 + 15) / 16 * 16;
+    plan.desc.push_back(o.d);
+    plan.host.push_back(std::move(o.h));
+    std::vector<uint8_t>().swap(o.tile);
+  }
+  return 0;
+}
+
+}  // namespace misob200

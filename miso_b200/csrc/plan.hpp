@@ -1,0 +1,73 @@
+// miso_b200/csrc/plan.hpp -- host-side plan: per-gene packed inputs of the chain kernel.
+//
+// A "plan" is everything the setup stage of the reference computes once per
+// gene before its MCMC loop (SURVEY.md section 8a, rows a-12 ... a-18), laid
+// out for the GPU:
+//   * compatibility codes   (splicing_matchIso / _paired, src/solve.c:8-218)
+//   * draw order            (splicing_order_matches, src/miso.c:988-993)
+//   * read classes          (splicing_i_miso_classes, src/miso_paired.c:576-681)
+//   * effective lengths, score tables (src/miso.c:773-784, miso_paired.c:396-419)
+// Paths are relative to /root/reference/pysplicing/.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/miso_b200.h"
+
+namespace misob200 {
+
+constexpr int kMaxIso = MISOB200_MAX_ISO;
+constexpr int kTilePadFront = 3;   // bytes in front of rank 0 (stream misalignment, see chain_kernel.cu)
+
+// Device-visible per-gene descriptor (one per gene, 16-byte aligned, POD).
+struct GeneDesc {
+  unsigned long long tile_off;   // byte offset of this gene's tile in the tile arena
+  long long sample_off;          // element offset into samples (f64)
+  long long loglik_off;          // element offset into loglik (f64)
+  long long drawn_off;           // element offset into the drawn-assignment arena (u8)
+  int K, R2, row_bytes, paired;
+  int n_fixed[kMaxIso];          // reads with exactly one compatible isoform
+  int L[kMaxIso];                // PE: lp(j) = L[k] - j  (miso_paired.c:409-410)
+  double offset[kMaxIso];        // SE log(effisolen_k) (miso.c:136) / PE assscores_k (miso_paired.c:418)
+  double hyper_m1[kMaxIso];      // alpha_k - 1 (miso.c:174)
+  double rs_se[kMaxIso];         // SE isoscores_k = -log(l_k) (miso.c:783)
+  double lg_sum, lg_each;        // lgamma(sum alpha), sum lgamma(alpha_k) (miso.c:177-178)
+  double sigma, sd, covar_const; // miso.c:328, :188, :101
+  double rp_fixed;               // read score of the single-isoform reads
+  unsigned gene_id;
+  int rp_always;                 // some read score is not finite: keep readProb in every MH ratio
+  int status;
+  int pad_;
+};
+
+struct GeneHost {
+  int K = 0, R = 0, R2 = 0, ncls = 0, status = 0;
+  long long read_base = 0;               // first read/pair of this gene in the plan-wide assignment output
+  std::vector<double> class_templates;   // ncls x K, row per class
+  std::vector<double> class_counts;
+  std::vector<int32_t> rank_read;        // rank -> read index (draw order of the reads that draw)
+  std::vector<int8_t> fixed_ass;         // per read: -1 incompatible, k single isoform, -2 drawn
+  std::vector<int32_t> codes, order;     // kept only when keep_match is on (parity tests)
+};
+
+struct Plan {
+  bool keep_match = false;
+  int paired = -1;                       // fixed by the first append
+  int read_len = 0, overhang = 1;
+  double frag_mean = 0, frag_var = 0, num_devs = 0;
+  int frag_start = 0, frag_len_n = 0;
+  std::vector<double> ptab;              // ptab[0] = 0, ptab[j+1] = fragment prob j (SE: {0,1})
+  std::vector<GeneDesc> desc;
+  std::vector<GeneHost> host;
+  std::vector<uint8_t> tiles;            // tile arena, each tile 16-byte aligned
+  long long n_reads = 0;
+  long long n_drawn = 0;
+  // device side (owned by run.cu)
+  void *dev = nullptr;
+};
+
+void set_error(const std::string &msg);
+int plan_append(Plan &plan, const misob200_reads_t &reads, int n_threads);
+
+}  // namespace misob200

@@ -1,0 +1,476 @@
+// miso_b200/csrc/run.cu -- device side of the C ABI: upload, chain kernels, download, summaries.
+//
+// One launch per isoform count K (the chain kernel is specialised on K so psi
+// and the cumulative sums stay in registers); genes of a bucket are dealt to
+// persistent warps through an atomic counter, longest first.  Buckets run on
+// separate streams so the tail of one overlaps the head of the next.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "chain_kernel.cuh"
+#include "plan.hpp"
+
+namespace misob200 {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+const char *last_error() { return g_error.c_str(); }
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+      return MISOB200_ECUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+struct DevState {
+  int device = 0;
+  misob200_params_t params{};
+  cudaStream_t stream = nullptr;            // copies + summary
+  cudaStream_t kstream[kMaxIso + 1] = {};   // one per K bucket
+  cudaEvent_t ev[6] = {};
+  cudaEvent_t kdone[kMaxIso + 1] = {};
+  uint8_t *d_tiles = nullptr;
+  GeneDesc *d_desc = nullptr;
+  double *d_ptab = nullptr;
+  double *d_samples = nullptr, *d_loglik = nullptr, *d_summary = nullptr;
+  uint8_t *d_drawn = nullptr;
+  int *d_accrej = nullptr;
+  unsigned *d_queue = nullptr;
+  int *d_items = nullptr;
+  std::vector<int> items[kMaxIso + 1];
+  int item_off[kMaxIso + 2] = {};
+  long long n_samples = 0, n_loglik = 0;
+  bool uploaded = false, have_run = false;
+  bool pinned_tiles = false, pinned_desc = false;
+  std::vector<uint8_t> h_drawn;
+  std::vector<int> h_accrej;
+  int sm_count = 0;
+};
+
+static int S_of(const misob200_params_t &p) { return p.lag > 0 ? (p.n_iters - p.burn_in) / p.lag : 0; }
+
+static int check_params(const misob200_params_t &p) {
+  if (p.n_iters < 0 || p.burn_in < 0 || p.lag < 1 || p.n_chains < 1 || p.burn_in > p.n_iters) {
+    set_error("invalid sampler parameters (iterations/burn-in/lag/chains)");
+    return MISOB200_EINVAL;
+  }
+  if (p.start != MISOB200_START_AUTO && p.start != MISOB200_START_UNIFORM) {
+    set_error("only MISO_START_AUTO and MISO_START_UNIFORM are implemented");
+    return MISOB200_UNIMPLEMENTED;
+  }
+  if (p.stop != MISOB200_STOP_FIXEDNO) {
+    set_error("only MISO_STOP_FIXEDNO is implemented");
+    return MISOB200_UNIMPLEMENTED;
+  }
+  if (p.algo != MISOB200_ALGO_REASSIGN) {
+    set_error("only MISO_ALGO_REASSIGN is implemented (the one misopy uses, miso_sampler.py:322)");
+    return MISOB200_UNIMPLEMENTED;
+  }
+  return 0;
+}
+
+void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, long long *n_loglik) {
+  const long long S = S_of(p);
+  long long so = 0, lo = 0;
+  for (size_t g = 0; g < plan.desc.size(); g++) {
+    plan.desc[g].sample_off = so;
+    plan.desc[g].loglik_off = lo;
+    so += (long long) plan.desc[g].K * p.n_chains * S;
+    lo += (long long) p.n_chains * S;
+  }
+  *n_samples = so; *n_loglik = lo;
+}
+
+static void free_dev(DevState *st) {
+  if (!st) return;
+  cudaSetDevice(st->device);
+  cudaFree(st->d_tiles); cudaFree(st->d_desc); cudaFree(st->d_ptab); cudaFree(st->d_samples);
+  cudaFree(st->d_loglik); cudaFree(st->d_summary); cudaFree(st->d_drawn); cudaFree(st->d_accrej);
+  cudaFree(st->d_queue); cudaFree(st->d_items);
+  for (auto &e : st->ev) if (e) cudaEventDestroy(e);
+  for (auto &e : st->kdone) if (e) cudaEventDestroy(e);
+  for (auto &s : st->kstream) if (s) cudaStreamDestroy(s);
+  if (st->stream) cudaStreamDestroy(st->stream);
+  delete st;
+}
+
+int release_device(Plan &plan) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  if (st) {
+    if (st->pinned_tiles) cudaHostUnregister(plan.tiles.data());
+    if (st->pinned_desc) cudaHostUnregister(plan.desc.data());
+    free_dev(st);
+  }
+  plan.dev = nullptr;
+  return 0;
+}
+
+int device_count(int *n) {
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { cudaGetLastError(); c = 0; }
+  if (n) *n = c;
+  return 0;
+}
+
+int device_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) +
+              " -- miso_b200 has no CPU path by design");
+    return MISOB200_ECUDA;
+  }
+  if (device < 0 || device >= n) { set_error("device ordinal out of range"); return MISOB200_EINVAL; }
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("miso_b200 is built for sm_100a only; device " + std::to_string(device) + " is sm_" +
+              std::to_string(prop.major) + std::to_string(prop.minor));
+    return MISOB200_ECUDA;
+  }
+  CK(cudaSetDevice(device));
+  return 0;
+}
+
+int upload(Plan &plan, const misob200_params_t &p) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  rc = device_init(p.device);
+  if (rc) return rc;
+  release_device(plan);
+  DevState *st = new DevState();
+  plan.dev = st;
+  st->device = p.device;
+  st->params = p;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, p.device));
+  st->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+  for (auto &e : st->ev) CK(cudaEventCreate(&e));
+  for (int k = 2; k <= kMaxIso; k++) {
+    CK(cudaStreamCreateWithFlags(&st->kstream[k], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&st->kdone[k], cudaEventDisableTiming));
+  }
+
+  plan_layout(plan, p, &st->n_samples, &st->n_loglik);
+  const size_t G = plan.desc.size();
+
+  // work lists: per K, genes ordered by decreasing number of drawing reads
+  int total = 0;
+  for (int k = 2; k <= kMaxIso; k++) {
+    auto &v = st->items[k];
+    v.clear();
+    for (size_t g = 0; g < G; g++)
+      if (plan.desc[g].K == k && plan.desc[g].status == 0) v.push_back((int) g);
+    std::stable_sort(v.begin(), v.end(),
+                     [&](int a, int b) { return plan.desc[a].R2 > plan.desc[b].R2; });
+    st->item_off[k] = total;
+    total += (int) v.size();
+  }
+  st->item_off[kMaxIso + 1] = total;
+
+  const size_t tile_bytes = plan.tiles.size();
+  CK(cudaMalloc(&st->d_tiles, std::max<size_t>(tile_bytes, 16)));
+  CK(cudaMalloc(&st->d_desc, std::max<size_t>(G, 1) * sizeof(GeneDesc)));
+  CK(cudaMalloc(&st->d_ptab, plan.ptab.size() * sizeof(double)));
+  CK(cudaMalloc(&st->d_samples, std::max<long long>(st->n_samples, 1) * sizeof(double)));
+  CK(cudaMalloc(&st->d_loglik, std::max<long long>(st->n_loglik, 1) * sizeof(double)));
+  CK(cudaMalloc(&st->d_summary, std::max<size_t>(G, 1) * MISOB200_SUMMARY_F64 * sizeof(double)));
+  CK(cudaMalloc(&st->d_drawn, std::max<long long>(plan.n_drawn, 16)));
+  CK(cudaMalloc(&st->d_accrej, std::max<size_t>(G, 1) * p.n_chains * 2 * sizeof(int)));
+  CK(cudaMalloc(&st->d_queue, (kMaxIso + 1) * sizeof(unsigned)));
+  CK(cudaMalloc(&st->d_items, std::max(total, 1) * sizeof(int)));
+
+  // pin the plan's arenas once so the per-run H2D runs at link speed
+  if (tile_bytes && cudaHostRegister(plan.tiles.data(), tile_bytes, cudaHostRegisterDefault) == cudaSuccess)
+    st->pinned_tiles = true;
+  if (G && cudaHostRegister(plan.desc.data(), G * sizeof(GeneDesc), cudaHostRegisterDefault) == cudaSuccess)
+    st->pinned_desc = true;
+  cudaGetLastError();
+
+  CK(cudaEventRecord(st->ev[0], st->stream));
+  if (tile_bytes) CK(cudaMemcpyAsync(st->d_tiles, plan.tiles.data(), tile_bytes, cudaMemcpyHostToDevice, st->stream));
+  if (G) CK(cudaMemcpyAsync(st->d_desc, plan.desc.data(), G * sizeof(GeneDesc), cudaMemcpyHostToDevice, st->stream));
+  CK(cudaMemcpyAsync(st->d_ptab, plan.ptab.data(), plan.ptab.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+  for (int k = 2; k <= kMaxIso; k++)
+    if (!st->items[k].empty())
+      CK(cudaMemcpyAsync(st->d_items + st->item_off[k], st->items[k].data(), st->items[k].size() * sizeof(int),
+                         cudaMemcpyHostToDevice, st->stream));
+  CK(cudaEventRecord(st->ev[1], st->stream));
+  CK(cudaStreamSynchronize(st->stream));
+  st->uploaded = true;
+  return 0;
+}
+
+template <int K>
+static int launch_bucket(Plan &plan, DevState *st, int *launches) {
+  const auto &v = st->items[K];
+  if (v.empty()) return 0;
+  constexpr int WARPS = 4;
+  int max_row = 0;
+  for (int g : v) max_row = std::max(max_row, plan.desc[g].row_bytes);
+  const int ptab_bytes = ((int) plan.ptab.size() * 8 + 15) & ~15;
+  int slot = max_row * (K + 1);
+  size_t smem = (size_t) ptab_bytes + WARPS * (16 + (size_t) slot);
+  const size_t smem_cap = 227 * 1024;
+  if (smem > smem_cap) { slot = 0; smem = (size_t) ptab_bytes + WARPS * 16; }   // stream tiles through L2
+  auto kern = chain_kernel<K, WARPS>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  if (per_sm < 1) { set_error("chain kernel does not fit on an SM"); return MISOB200_ECUDA; }
+  const long long n_items = (long long) v.size() * st->params.n_chains;
+  long long blocks = (n_items + WARPS - 1) / WARPS;
+  blocks = std::min<long long>(blocks, (long long) per_sm * st->sm_count);
+
+  ChainParams P;
+  P.desc = st->d_desc;
+  P.items = st->d_items + st->item_off[K];
+  P.n_genes = (int) v.size();
+  P.n_chains = st->params.n_chains;
+  P.tiles = st->d_tiles;
+  P.ptab = st->d_ptab;
+  P.n_ptab = (int) plan.ptab.size();
+  P.samples = st->d_samples;
+  P.loglik = st->d_loglik;
+  P.drawn = st->d_drawn;
+  P.accrej = st->d_accrej;
+  P.queue = st->d_queue + K;
+  P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
+  P.start = st->params.start;
+  P.key.k0 = (uint32_t) st->params.seed; P.key.k1 = (uint32_t) (st->params.seed >> 32);
+  P.slot_bytes = slot;
+  kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[K]>>>(P);
+  CK(cudaGetLastError());
+  (*launches)++;
+  return 0;
+}
+
+int run_resident(Plan &plan, double *kernel_ms, int *launches) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  if (!st || !st->uploaded) { set_error("run_resident: plan is not on the device (call misob200_upload)"); return MISOB200_EINVAL; }
+  CK(cudaSetDevice(st->device));
+  int nl = 0;
+  CK(cudaMemsetAsync(st->d_queue, 0, (kMaxIso + 1) * sizeof(unsigned), st->stream));
+  // recorded samples that a short chain never writes stay zero, like the
+  // reference's zero-initialised sample matrix
+  CK(cudaMemsetAsync(st->d_samples, 0, std::max<long long>(st->n_samples, 1) * sizeof(double), st->stream));
+  CK(cudaMemsetAsync(st->d_loglik, 0, std::max<long long>(st->n_loglik, 1) * sizeof(double), st->stream));
+  CK(cudaEventRecord(st->ev[2], st->stream));
+  int rc = 0;
+  // big-K buckets first: they have the longest chains
+  for (int k = kMaxIso; k >= 2 && !rc; k--) {
+    if (st->items[k].empty()) continue;
+    CK(cudaStreamWaitEvent(st->kstream[k], st->ev[2], 0));
+    switch (k) {
+      case 2: rc = launch_bucket<2>(plan, st, &nl); break;
+      case 3: rc = launch_bucket<3>(plan, st, &nl); break;
+      case 4: rc = launch_bucket<4>(plan, st, &nl); break;
+      case 5: rc = launch_bucket<5>(plan, st, &nl); break;
+      case 6: rc = launch_bucket<6>(plan, st, &nl); break;
+      case 7: rc = launch_bucket<7>(plan, st, &nl); break;
+      case 8: rc = launch_bucket<8>(plan, st, &nl); break;
+    }
+    if (rc) return rc;
+    CK(cudaEventRecord(st->kdone[k], st->kstream[k]));
+    CK(cudaStreamWaitEvent(st->stream, st->kdone[k], 0));
+  }
+  CK(cudaEventRecord(st->ev[3], st->stream));
+  CK(cudaStreamSynchronize(st->stream));
+  CK(cudaGetLastError());
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, st->ev[2], st->ev[3]));
+  if (kernel_ms) *kernel_ms = ms;
+  if (launches) *launches = nl;
+  st->have_run = true;
+  return 0;
+}
+
+int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, int32_t *rundata,
+             int32_t *status) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  if (!st || !st->have_run) { set_error("download: nothing has run"); return MISOB200_EINVAL; }
+  CK(cudaSetDevice(st->device));
+  const size_t G = plan.desc.size();
+  const misob200_params_t &p = st->params;
+  st->h_drawn.resize(std::max<long long>(plan.n_drawn, 1));
+  st->h_accrej.resize(std::max<size_t>(G, 1) * p.n_chains * 2);
+  CK(cudaEventRecord(st->ev[4], st->stream));
+  if (samples && st->n_samples)
+    CK(cudaMemcpyAsync(samples, st->d_samples, st->n_samples * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+  if (loglik && st->n_loglik)
+    CK(cudaMemcpyAsync(loglik, st->d_loglik, st->n_loglik * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+  if (assignment && plan.n_drawn)
+    CK(cudaMemcpyAsync(st->h_drawn.data(), st->d_drawn, plan.n_drawn, cudaMemcpyDeviceToHost, st->stream));
+  if (G)
+    CK(cudaMemcpyAsync(st->h_accrej.data(), st->d_accrej, G * p.n_chains * 2 * sizeof(int), cudaMemcpyDeviceToHost, st->stream));
+  CK(cudaEventRecord(st->ev[5], st->stream));
+  CK(cudaStreamSynchronize(st->stream));
+
+  // host epilogue: scatter chain-0 assignments back to input read order
+  // (miso.c:943-946) and fill rundata (include/splicing.h:143-146)
+  auto epilogue = [&](size_t g0, size_t g1) {
+    for (size_t g = g0; g < g1; g++) {
+      const GeneHost &h = plan.host[g];
+      const GeneDesc &d = plan.desc[g];
+      if (status) status[g] = h.status;
+      if (rundata) {
+        int acc = 0, rej = 0;
+        if (h.status == 0)
+          for (int c = 0; c < p.n_chains; c++) {
+            acc += st->h_accrej[(g * p.n_chains + c) * 2];
+            rej += st->h_accrej[(g * p.n_chains + c) * 2 + 1];
+          }
+        int32_t *rd = rundata + g * 9;
+        rd[0] = h.K; rd[1] = p.n_iters; rd[2] = 0; rd[3] = p.burn_in; rd[4] = p.lag;
+        rd[5] = acc; rd[6] = rej; rd[7] = p.n_chains;
+        rd[8] = (int) ((long long) p.n_chains * (p.n_iters - p.burn_in) / p.lag);
+      }
+      if (assignment) {
+        int32_t *a = assignment + h.read_base;
+        for (int r = 0; r < h.R; r++) a[r] = h.status == 0 ? h.fixed_ass[r] : -1;
+        if (h.status == 0) {
+          const uint8_t *dr = st->h_drawn.data() + d.drawn_off;
+          for (int i = 0; i < h.R2; i++) a[h.rank_read[i]] = dr[i];
+        }
+      }
+    }
+  };
+  unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+  if (G < 256) nt = 1;
+  if (nt == 1) epilogue(0, G);
+  else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++) pool.emplace_back(epilogue, G * t / nt, G * (t + 1) / nt);
+    for (auto &t : pool) t.join();
+  }
+  return 0;
+}
+
+// ---- posterior summaries --------------------------------------------------
+// One CTA per gene: mean over the C*S recorded samples and the 95% credible
+// interval by order statistics, indices int(round(0.025 n)) - 1 and
+// int(round(0.975 n)) - 1 of the sorted samples with Python-2 rounding (half
+// away from zero) -- /root/reference/misopy/credible_intervals.py:31-55 --
+// plus the per-isoform assigned-read counts of chain 0.
+__global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, int S,
+                               const double *samples, const uint8_t *drawn, const int *accrej,
+                               double *summary) {
+  extern __shared__ double vals[];
+  const int g = blockIdx.x;
+  if (g >= n_genes) return;
+  const GeneDesc &d = desc[g];
+  double *out = summary + (size_t) g * MISOB200_SUMMARY_F64;
+  const int n = n_chains * S, K = d.K;
+  int *iout = reinterpret_cast<int *>(out + 24);
+  if (d.status != 0) {
+    for (int i = threadIdx.x; i < MISOB200_SUMMARY_F64; i += blockDim.x) out[i] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) { iout[8] = K; iout[11] = d.status; }
+    return;
+  }
+  __shared__ int s_cnt[kMaxIso];
+  __shared__ double s_red[32];
+  if (threadIdx.x < kMaxIso) s_cnt[threadIdx.x] = threadIdx.x < K ? d.n_fixed[threadIdx.x] : 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < d.R2; i += blockDim.x) {
+    const int a = drawn[d.drawn_off + i];
+    if (a < K) atomicAdd(&s_cnt[a], 1);
+  }
+  const int lo = (int) floor(0.025 * n + 0.5) - 1, hi = (int) floor(0.975 * n + 0.5) - 1;
+  for (int k = 0; k < kMaxIso; k++) {
+    double mean = 0.0, vlo = 0.0, vhi = 0.0;
+    if (k < K && n > 0) {
+      double part = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = samples[d.sample_off + (long long) i * K + k];
+        vals[i] = v;
+        part += v;
+      }
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int) (blockDim.x >> 5); w++) t += s_red[w];
+        s_red[0] = t / n;
+      }
+      __syncthreads();
+      mean = s_red[0];
+      // rank selection: element with exactly `lo` (`hi`) elements before it
+      // in the stable order (value, index)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = vals[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+          const double w = vals[j];
+          rank += (w < v) || (w == v && j < i);
+        }
+        if (rank == (lo < 0 ? n + lo : lo)) s_red[1] = v;      // Python index -1 wraps
+        if (rank == (hi < 0 ? n + hi : hi)) s_red[2] = v;
+      }
+      __syncthreads();
+      vlo = s_red[1]; vhi = s_red[2];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[k] = mean; out[8 + k] = vlo; out[16 + k] = vhi; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0, rej = 0;
+    for (int c = 0; c < n_chains; c++) {
+      acc += accrej[((size_t) g * n_chains + c) * 2];
+      rej += accrej[((size_t) g * n_chains + c) * 2 + 1];
+    }
+    for (int k = 0; k < kMaxIso; k++) iout[k] = s_cnt[k];
+    iout[8] = K; iout[9] = acc; iout[10] = rej; iout[11] = 0;
+    for (int k = 12; k < 16; k++) iout[k] = 0;
+  }
+}
+
+int summarize(Plan &plan, double *summary) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  if (!st || !st->have_run) { set_error("summarize: nothing has run"); return MISOB200_EINVAL; }
+  CK(cudaSetDevice(st->device));
+  const int G = (int) plan.desc.size();
+  if (G == 0) return 0;
+  const int S = S_of(st->params), n = st->params.n_chains * S;
+  const size_t smem = std::max(n, 1) * sizeof(double);
+  if (smem > 200 * 1024) { set_error("summarize: too many samples per gene for the on-chip selection"); return MISOB200_UNIMPLEMENTED; }
+  CK(cudaFuncSetAttribute(summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, S, st->d_samples, st->d_drawn,
+                                              st->d_accrej, st->d_summary);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(summary, st->d_summary, (size_t) G * MISOB200_SUMMARY_F64 * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
+  CK(cudaStreamSynchronize(st->stream));
+  return 0;
+}
+
+void *device_summary_ptr(Plan &plan) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  return st ? st->d_summary : nullptr;
+}
+
+int run_timing(Plan &plan, double *timing_ms) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  if (!st || !timing_ms) return 0;
+  float h2d = 0, k = 0, d2h = 0, tot = 0;
+  cudaEventElapsedTime(&h2d, st->ev[0], st->ev[1]);
+  cudaEventElapsedTime(&k, st->ev[2], st->ev[3]);
+  cudaEventElapsedTime(&d2h, st->ev[4], st->ev[5]);
+  cudaEventElapsedTime(&tot, st->ev[0], st->ev[5]);
+  timing_ms[0] = h2d; timing_ms[1] = k; timing_ms[2] = d2h; timing_ms[3] = tot;
+  return 0;
+}
+
+}  // namespace misob200

@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def port():
+    """oracle/libmiso_oracle.so, the plain-C restatement (built on demand: gcc only)."""
+    import subprocess
+    import refdriver
+    if not refdriver.port_available():
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
+    return refdriver.PortOracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """oracle/_ref/libsplicing_ref.so, the unmodified reference C (skipped if never built)."""
+    import refdriver
+    if not refdriver.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return refdriver.RefOracle()
