@@ -175,6 +175,12 @@ int misob200_download(misob200_plan_t *plan, double *samples, double *loglik,
 		      int32_t *assignment, int32_t *rundata, int32_t *status);
 int misob200_release_device(misob200_plan_t *plan);
 
+/* measurement helpers: kernel time of each K bucket of the last resident run
+   (ms9[K], K = 2..8, CUDA events on that bucket's stream) and the bytes one
+   misob200_run moves over PCIe in each direction */
+int misob200_bucket_timing(misob200_plan_t *plan, double *ms9);
+int misob200_transfer_bytes(misob200_plan_t *plan, int64_t *h2d, int64_t *d2h);
+
 /* Posterior summaries on the device (needs a resident run): per gene a
    256-byte record {mean[8], ci_low[8], ci_high[8] (f64); assigned_counts[8],
    n_iso, accepted, rejected, status (i32); pad}.  summary: n_genes*32 f64. */

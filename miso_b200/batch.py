@@ -274,6 +274,16 @@ class Plan:
         check(lib.misob200_summarize(self.h, ptr(s)))
         return s[:G]
 
+    def bucket_timing(self):
+        ms = np.zeros(9)
+        check(lib.misob200_bucket_timing(self.h, ptr(ms)))
+        return ms
+
+    def transfer_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(lib.misob200_transfer_bytes(self.h, C.addressof(a), C.addressof(b)))
+        return a.value, b.value
+
     def release_device(self):
         lib.misob200_release_device(self.h)
 

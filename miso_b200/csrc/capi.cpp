@@ -17,6 +17,9 @@ int release_device(Plan &plan);
 int summarize(Plan &plan, double *summary);
 int run_timing(Plan &plan, double *timing_ms);
 int device_count(int *n);
+int bucket_timing(Plan &plan, double *ms);
+long long input_bytes(const Plan &plan);
+long long output_bytes(Plan &plan);
 }  // namespace misob200
 
 using namespace misob200;
@@ -168,6 +171,16 @@ int misob200_run(misob200_plan_t *plan, const misob200_params_t *params, double 
   if (int rc = run_resident(plan->p, nullptr, launches)) return rc;
   if (int rc = download(plan->p, samples, loglik, assignment, rundata, status)) return rc;
   run_timing(plan->p, timing_ms);
+  return 0;
+}
+int misob200_bucket_timing(misob200_plan_t *plan, double *ms9) {
+  if (!plan || !ms9) return MISOB200_EINVAL;
+  return bucket_timing(plan->p, ms9);
+}
+int misob200_transfer_bytes(misob200_plan_t *plan, int64_t *h2d, int64_t *d2h) {
+  if (!plan) return MISOB200_EINVAL;
+  if (h2d) *h2d = input_bytes(plan->p);
+  if (d2h) *d2h = output_bytes(plan->p);
   return 0;
 }
 int misob200_summarize(misob200_plan_t *plan, double *summary) {

@@ -94,89 +94,170 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
+// ---- explicit address-space loads ------------------------------------------------
+// The tile normally sits in shared memory (32-bit shared addresses, LDS); genes
+// whose tile does not fit in a slot are streamed from global/L2 instead.
+template <bool SMEM> struct TileMem;
+template <> struct TileMem<true> {
+  using addr_t = uint32_t;
+  static __device__ __forceinline__ addr_t base(const void *p) { return smem_u32(p); }
+  static __device__ __forceinline__ uint32_t ld(addr_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+  }
+};
+template <> struct TileMem<false> {
+  using addr_t = const unsigned char *;
+  static __device__ __forceinline__ addr_t base(const void *p) { return static_cast<addr_t>(p); }
+  static __device__ __forceinline__ uint32_t ld(addr_t a) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(a));
+    return v;
+  }
+};
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
 // ---- one reassignment pass ----------------------------------------------------
 // src/miso.c:30-91 / src/miso_paired.c:24-86 for the R2 reads that draw.
 // Lane handles Philox block Q0+T (uniform indices 4(Q0+T)..+3) for
 // T = lane + 32*step, i.e. ranks 4T-o .. 4T-o+3 with o = n_u & 3: the stream is
 // sequential (the accept draw is conditional, miso.c:870), so a pass starts at
 // an arbitrary phase o.  Rows carry 3 zero bytes in front and zero padding
-// behind; a zero code is "incompatible", so phantom ranks choose nothing.
+// behind; a zero code means "incompatible" (weight psi_k * ptab[0] = 0).
+//
+// Choice rule.  With C_k the running sum of psi_k * p_k over ALL isoforms
+// (incompatible ones add an exact 0.0, so C_k is the reference's cumsum at the
+// last compatible isoform <= k) and rnd = u * C_{K-1}:
+//   >= 3 compatible: first w with !(rnd > cumsum[w])      (miso.c:78)
+//      2 compatible: rnd <  cumsum[0] ? first : second    (miso.c:71)
+// Both are "the number of k < K-1 whose test says go on": rnd > C_k, resp.
+// rnd >= C_k, and rnd >= C  <=>  nextup(rnd) > C for rnd >= 0 -- one integer add
+// on the bit pattern per read.  (Leading incompatible isoforms have C_k = 0 <
+// rnd and are skipped, the others repeat their predecessor's verdict.)  So the
+// pass only keeps G_k = #{reads with test_k true}; the per-isoform counts the MH
+// ratio needs are n_0 = R2 - G_0, n_k = G_{k-1} - G_k, n_{K-1} = G_{K-2}.
+// Phantom ranks (padding) have rnd = 0 and C_k = 0: no test is true.
+// The argument needs 0 < rnd < C_{K-1}, true whenever C_{K-1} is a normal number
+// (u is in [2^-33, 1 - 2^-33]); a read whose weights all but underflow
+// (C_{K-1} < 1e-290) sends the whole pass to the literal rule below (MODE 3).
 //   MODE 0: counts only.  MODE 1: + read score of the chosen isoform
 //   (miso_paired.c:157-163), needed when the next iteration records.
 //   MODE 2: + write the chosen isoform per rank (final assignment, chain 0).
-template <int K, int MODE>
-__device__ __forceinline__ void reassign_pass(const uint32_t *__restrict__ rows, int row_words,
-                                              const double *__restrict__ ptab, const double (&psi)[K],
+//   MODE 3: literal per-read rule with validity tests (degenerate weights).
+template <int K, int MODE, bool SMEM>
+__device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes,
+                                              uint32_t ptab_s, const double (&psi)[K],
                                               unsigned long long n_u, int R2, uint32_t gene,
                                               uint32_t chain, PhiloxKey key, int paired,
-                                              const int (&L)[K], int (&cnt)[K], double &rp,
+                                              const int *__restrict__ L, int (&cnt)[K], double &rp,
                                               uint8_t *__restrict__ ass_out) {
+  using TM = TileMem<SMEM>;
   const int lane = threadIdx.x & 31;
   const int o = (int) (n_u & 3ull);
   const uint32_t Q0 = (uint32_t) (n_u >> 2);
   const int nsteps = (R2 + o + 127) >> 7;
   const uint32_t sel = 0x3210u + 0x1111u * (uint32_t) (3 - o);
+  int G[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) cnt[k] = 0;
+  for (int k = 0; k < K; k++) G[k] = 0;
   double rp_lane = 0.0;
+  bool degenerate = false;
+  typename TM::addr_t a = rows + 4 * lane;
 
   for (int s = 0; s < nsteps; s++) {
     const int T = lane + 32 * s;
     uint32_t x[4];
     philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key.k0, key.k1, x);
-    uint32_t cw[K];
+    uint32_t cw[K + 1];
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-      const uint32_t w0 = rows[k * row_words + T], w1 = rows[k * row_words + T + 1];
+    for (int k = 0; k <= K; k++) {
+      const uint32_t w0 = TM::ld(a + k * row_bytes), w1 = TM::ld(a + k * row_bytes + 4);
       cw[k] = __byte_perm(w0, w1, sel);
     }
-    const uint32_t fw = __byte_perm(rows[K * row_words + T], rows[K * row_words + T + 1], sel);
+    a += 128;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const bool two = ((fw >> (8 * i)) & 0xffu) == 1u;     // exactly two compatible isoforms
+      const uint32_t flag = __byte_perm(cw[K], 0u, 0x4440u | (uint32_t) i);
       double S = 0.0, C[K];
       uint32_t code[K];
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        code[k] = (cw[k] >> (8 * i)) & 0xffu;
-        S = S + psi[k] * ptab[code[k]];                     // CUMSUM, miso_paired.c:11-22
+        code[k] = __byte_perm(cw[k], 0u, 0x4440u | (uint32_t) i);
+        S = S + psi[k] * lds_f64(ptab_s + code[k] * 8u);     // CUMSUM, miso_paired.c:11-22
         C[k] = S;
       }
-      const double rnd = uniform_from_word(x[i]) * S;       // miso.c:70,76
-      int chosen = -1;
-      uint32_t ccode = 0;
-      int Lc = 0;
+      const double rnd = uniform_from_word(x[i]) * S;          // miso.c:70,76
+      if (MODE != 3) {
+        // two compatible isoforms: compare with nextup(rnd), see above
+        const double rc = __longlong_as_double(__double_as_longlong(rnd) + (long long) (flag == 1u));
+        // S this small: u*S may round to 0 or to S itself -- outside the argument above
+        if (flag != 0u && !(S >= 1e-290)) degenerate = true;
+        int chosen = 0;
 #pragma unroll
-      for (int k = K - 1; k >= 0; k--) {
-        const bool valid = code[k] != 0u;
-        // noValid == 2: rand < cumsum[0] (miso.c:71); else first rand <= cumsum[w] (miso.c:78)
-        const bool hit = two ? (rnd < C[k]) : (rnd <= C[k]);
-        if (valid && (hit || chosen < 0)) {
-          chosen = k;
-          if (MODE == 1) { ccode = code[k]; Lc = L[k]; }
+        for (int k = 0; k < K - 1; k++) {
+          const bool go_on = rc > C[k];
+          G[k] += go_on;
+          if (MODE != 0) chosen += go_on;
         }
-      }
+        if (MODE == 1 || MODE == 2) {
+          const int rank = 4 * T - o + i;
+          const bool real = rank >= 0 && rank < R2;
+          if (MODE == 1 && real && paired) {
+            uint32_t cc = code[0];
 #pragma unroll
-      for (int k = 0; k < K; k++) cnt[k] += (chosen == k);
-      if (MODE == 1) {
+            for (int k = 1; k < K; k++)
+              if (chosen == k) cc = code[k];
+            const int Lc = __ldg(L + chosen);
+            const double lp = (double) (Lc - ((int) cc - 1));
+            rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
+          }
+          if (MODE == 2 && real) ass_out[rank] = (uint8_t) chosen;
+        }
+      } else {
+        const bool two = flag == 1u;
+        int chosen = -1;
+        uint32_t cc = 0;
+#pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+          const bool valid = code[k] != 0u;
+          const bool hit = two ? (rnd < C[k]) : (rnd <= C[k]);
+          if (valid && (hit || chosen < 0)) { chosen = k; cc = code[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) G[k] += (chosen == k);
         if (chosen >= 0 && paired) {
-          const double lp = (double) (Lc - ((int) ccode - 1));
-          rp_lane += -log(lp) + ptab[ccode];                // isoscores, miso_paired.c:409-411
+          const int Lc = __ldg(L + chosen);
+          const double lp = (double) (Lc - ((int) cc - 1));
+          rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);
         }
-      }
-      if (MODE == 2) {
         const int rank = 4 * T - o + i;
-        if (rank >= 0 && rank < R2) ass_out[rank] = (uint8_t) chosen;
+        if (ass_out && rank >= 0 && rank < R2) ass_out[rank] = (uint8_t) chosen;
       }
     }
   }
+  if (MODE != 3) {
+    if (__any_sync(0xffffffffu, degenerate)) return false;
 #pragma unroll
-  for (int k = 0; k < K; k++) cnt[k] = __reduce_add_sync(0xffffffffu, cnt[k]);
-  if (MODE == 1) {
+    for (int k = 0; k < K - 1; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]);
+    cnt[0] = R2 - G[0];
+#pragma unroll
+    for (int k = 1; k < K - 1; k++) cnt[k] = G[k - 1] - G[k];
+    cnt[K - 1] = G[K - 2];
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; k++) cnt[k] = __reduce_add_sync(0xffffffffu, G[k]);
+  }
+  if (MODE == 1 || MODE == 3) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
     rp = rp_lane;
   }
+  return true;
 }
 
 // Everything derived from a candidate alpha (lane i < K-1 holds alpha_i).
@@ -251,9 +332,9 @@ __device__ __forceinline__ double count_dot(int cnt_k, double v_k) {
   return s;
 }
 
-template <int K>
+template <int K, bool SMEM>
 __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_index, int chain,
-                          const uint32_t *rows, const double *ptab) {
+                          typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s) {
   constexpr int len = K - 1;
   const int lane = threadIdx.x & 31;
   const int kk = lane < K ? lane : K - 1;
@@ -263,12 +344,10 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   const int nfix_k = d.n_fixed[kk];
   const double lg_sum = d.lg_sum, lg_each = d.lg_each;
   const double sigma = d.sigma, sd = d.sd, covar = d.covar_const;
-  const int R2 = d.R2, row_words = d.row_bytes >> 2, paired = d.paired;
+  const int R2 = d.R2, row_bytes = d.row_bytes, paired = d.paired;
   const uint32_t gid = d.gene_id;
   const PhiloxKey key = P.key;
-  int L[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) L[k] = d.L[k];
+  const int *L = d.L;
 
   unsigned long long n_u = 0;
   // ---- start state, splicing_drift_proposal_init (miso.c:330-447) ----------
@@ -308,21 +387,25 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     for (int k = 0; k < K; k++) psi_r[k] = shfl_d(cur.psi, k);
     const bool last = (m_next >= P.n_iters);
     const bool rec_next = d.rp_always || (paired && m_next >= P.burn_in && lagc == P.lag - 1);
+    bool ok;
     if (last && ass_out)
-      reassign_pass<K, 2>(rows, row_words, ptab, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
-                          cnt, rp_drawn, ass_out);
+      ok = reassign_pass<K, 2, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
+                                     paired, L, cnt, rp_drawn, ass_out);
     else if (rec_next && !last)
-      reassign_pass<K, 1>(rows, row_words, ptab, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
-                          cnt, rp_drawn, ass_out);
+      ok = reassign_pass<K, 1, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
+                                     paired, L, cnt, rp_drawn, ass_out);
     else
-      reassign_pass<K, 0>(rows, row_words, ptab, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
-                          cnt, rp_drawn, ass_out);
+      ok = reassign_pass<K, 0, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
+                                     paired, L, cnt, rp_drawn, ass_out);
+    if (!ok)   // some read's weights all underflowed: redo the pass with the literal rule
+      reassign_pass<K, 3, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired,
+                                L, cnt, rp_drawn, last ? ass_out : nullptr);
     n_u += (unsigned long long) R2;
     int c = 0;
 #pragma unroll
     for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
     cnt_k = c + nfix_k;
-    return rec_next;
+    return rec_next || !ok;
   };
 
   bool have_rp = do_pass(0);     // initial assignment (miso.c:840-843)
@@ -393,7 +476,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
 }
 
 template <int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) chain_kernel(const ChainParams P) {
+__global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(const ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // layout: [ptab | per-warp {mbarrier(16 B), tile slot}]
@@ -418,7 +501,6 @@ __global__ void __launch_bounds__(WARPS * 32) chain_kernel(const ChainParams P) 
     const int chain = (int) (item % P.n_chains);
     const GeneDesc &d = P.desc[gi];
     const uint32_t tile_bytes = (uint32_t) d.row_bytes * (K + 1);
-    const uint32_t *rows;
     if (P.slot_bytes) {
       __syncwarp();
       if (lane == 0) {
@@ -428,11 +510,10 @@ __global__ void __launch_bounds__(WARPS * 32) chain_kernel(const ChainParams P) 
       }
       mbar_wait(bar, phase);
       phase ^= 1u;
-      rows = reinterpret_cast<const uint32_t *>(slot);
+      run_chain<K, true>(P, d, gi, chain, TileMem<true>::base(slot), smem_u32(s_ptab));
     } else {
-      rows = reinterpret_cast<const uint32_t *>(P.tiles + d.tile_off);
+      run_chain<K, false>(P, d, gi, chain, TileMem<false>::base(P.tiles + d.tile_off), smem_u32(s_ptab));
     }
-    run_chain<K>(P, d, gi, chain, rows, s_ptab);
   }
 }
 

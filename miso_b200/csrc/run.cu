@@ -38,6 +38,7 @@ struct DevState {
   cudaStream_t kstream[kMaxIso + 1] = {};   // one per K bucket
   cudaEvent_t ev[6] = {};
   cudaEvent_t kdone[kMaxIso + 1] = {};
+  cudaEvent_t kbeg[kMaxIso + 1] = {}, kend[kMaxIso + 1] = {};
   uint8_t *d_tiles = nullptr;
   GeneDesc *d_desc = nullptr;
   double *d_ptab = nullptr;
@@ -98,6 +99,9 @@ static void free_dev(DevState *st) {
   cudaFree(st->d_queue); cudaFree(st->d_items);
   for (auto &e : st->ev) if (e) cudaEventDestroy(e);
   for (auto &e : st->kdone) if (e) cudaEventDestroy(e);
+  for (auto &e : st->kbeg) if (e) cudaEventDestroy(e);
+  for (auto &e : st->kend) if (e) cudaEventDestroy(e);
+  if (!st->h_drawn.empty()) { cudaHostUnregister(st->h_drawn.data()); cudaGetLastError(); }
   for (auto &s : st->kstream) if (s) cudaStreamDestroy(s);
   if (st->stream) cudaStreamDestroy(st->stream);
   delete st;
@@ -142,9 +146,41 @@ int device_init(int device) {
   return 0;
 }
 
+static int copy_inputs(Plan &plan, DevState *st) {
+  const size_t G = plan.desc.size(), tile_bytes = plan.tiles.size();
+  CK(cudaEventRecord(st->ev[0], st->stream));
+  if (tile_bytes) CK(cudaMemcpyAsync(st->d_tiles, plan.tiles.data(), tile_bytes, cudaMemcpyHostToDevice, st->stream));
+  if (G) CK(cudaMemcpyAsync(st->d_desc, plan.desc.data(), G * sizeof(GeneDesc), cudaMemcpyHostToDevice, st->stream));
+  CK(cudaMemcpyAsync(st->d_ptab, plan.ptab.data(), plan.ptab.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+  for (int k = 2; k <= kMaxIso; k++)
+    if (!st->items[k].empty())
+      CK(cudaMemcpyAsync(st->d_items + st->item_off[k], st->items[k].data(), st->items[k].size() * sizeof(int),
+                         cudaMemcpyHostToDevice, st->stream));
+  CK(cudaEventRecord(st->ev[1], st->stream));
+  CK(cudaStreamSynchronize(st->stream));
+  st->uploaded = true;
+  st->have_run = false;
+  return 0;
+}
+
+long long input_bytes(const Plan &plan) {
+  long long b = (long long) plan.tiles.size() + (long long) plan.desc.size() * (sizeof(GeneDesc) + sizeof(int)) +
+                (long long) plan.ptab.size() * sizeof(double);
+  return b;
+}
+
 int upload(Plan &plan, const misob200_params_t &p) {
   int rc = check_params(p);
   if (rc) return rc;
+  if (plan.dev) {
+    // same plan, same parameters: keep the device buffers and the pinned
+    // registration, only redo the host->device copies
+    DevState *old = static_cast<DevState *>(plan.dev);
+    if (std::memcmp(&old->params, &p, sizeof(p)) == 0) {
+      CK(cudaSetDevice(old->device));
+      return copy_inputs(plan, old);
+    }
+  }
   rc = device_init(p.device);
   if (rc) return rc;
   release_device(plan);
@@ -160,6 +196,8 @@ int upload(Plan &plan, const misob200_params_t &p) {
   for (int k = 2; k <= kMaxIso; k++) {
     CK(cudaStreamCreateWithFlags(&st->kstream[k], cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&st->kdone[k], cudaEventDisableTiming));
+    CK(cudaEventCreate(&st->kbeg[k]));
+    CK(cudaEventCreate(&st->kend[k]));
   }
 
   plan_layout(plan, p, &st->n_samples, &st->n_loglik);
@@ -197,19 +235,10 @@ int upload(Plan &plan, const misob200_params_t &p) {
   if (G && cudaHostRegister(plan.desc.data(), G * sizeof(GeneDesc), cudaHostRegisterDefault) == cudaSuccess)
     st->pinned_desc = true;
   cudaGetLastError();
-
-  CK(cudaEventRecord(st->ev[0], st->stream));
-  if (tile_bytes) CK(cudaMemcpyAsync(st->d_tiles, plan.tiles.data(), tile_bytes, cudaMemcpyHostToDevice, st->stream));
-  if (G) CK(cudaMemcpyAsync(st->d_desc, plan.desc.data(), G * sizeof(GeneDesc), cudaMemcpyHostToDevice, st->stream));
-  CK(cudaMemcpyAsync(st->d_ptab, plan.ptab.data(), plan.ptab.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
-  for (int k = 2; k <= kMaxIso; k++)
-    if (!st->items[k].empty())
-      CK(cudaMemcpyAsync(st->d_items + st->item_off[k], st->items[k].data(), st->items[k].size() * sizeof(int),
-                         cudaMemcpyHostToDevice, st->stream));
-  CK(cudaEventRecord(st->ev[1], st->stream));
-  CK(cudaStreamSynchronize(st->stream));
-  st->uploaded = true;
-  return 0;
+  st->h_drawn.resize(std::max<long long>(plan.n_drawn, 1));
+  st->h_accrej.resize(std::max<size_t>(G, 1) * p.n_chains * 2);
+  if (cudaHostRegister(st->h_drawn.data(), st->h_drawn.size(), cudaHostRegisterDefault) != cudaSuccess) cudaGetLastError();
+  return copy_inputs(plan, st);
 }
 
 template <int K>
@@ -272,6 +301,7 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
   for (int k = kMaxIso; k >= 2 && !rc; k--) {
     if (st->items[k].empty()) continue;
     CK(cudaStreamWaitEvent(st->kstream[k], st->ev[2], 0));
+    CK(cudaEventRecord(st->kbeg[k], st->kstream[k]));
     switch (k) {
       case 2: rc = launch_bucket<2>(plan, st, &nl); break;
       case 3: rc = launch_bucket<3>(plan, st, &nl); break;
@@ -282,6 +312,7 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
       case 8: rc = launch_bucket<8>(plan, st, &nl); break;
     }
     if (rc) return rc;
+    CK(cudaEventRecord(st->kend[k], st->kstream[k]));
     CK(cudaEventRecord(st->kdone[k], st->kstream[k]));
     CK(cudaStreamWaitEvent(st->stream, st->kdone[k], 0));
   }
@@ -303,8 +334,6 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
   CK(cudaSetDevice(st->device));
   const size_t G = plan.desc.size();
   const misob200_params_t &p = st->params;
-  st->h_drawn.resize(std::max<long long>(plan.n_drawn, 1));
-  st->h_accrej.resize(std::max<size_t>(G, 1) * p.n_chains * 2);
   CK(cudaEventRecord(st->ev[4], st->stream));
   if (samples && st->n_samples)
     CK(cudaMemcpyAsync(samples, st->d_samples, st->n_samples * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
@@ -459,6 +488,27 @@ int summarize(Plan &plan, double *summary) {
 void *device_summary_ptr(Plan &plan) {
   DevState *st = static_cast<DevState *>(plan.dev);
   return st ? st->d_summary : nullptr;
+}
+
+// per-bucket kernel durations of the last resident run, ms[k] for K = 0..8 (0 when unused)
+int bucket_timing(Plan &plan, double *ms) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  if (!st || !st->have_run) { set_error("bucket_timing: nothing has run"); return MISOB200_EINVAL; }
+  for (int k = 0; k <= kMaxIso; k++) {
+    ms[k] = 0.0;
+    if (k >= 2 && !st->items[k].empty()) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, st->kbeg[k], st->kend[k]) == cudaSuccess) ms[k] = t;
+      else cudaGetLastError();
+    }
+  }
+  return 0;
+}
+
+long long output_bytes(Plan &plan) {
+  DevState *st = static_cast<DevState *>(plan.dev);
+  if (!st) return 0;
+  return (st->n_samples + st->n_loglik) * 8 + plan.n_drawn + (long long) plan.desc.size() * st->params.n_chains * 8;
 }
 
 int run_timing(Plan &plan, double *timing_ms) {
