@@ -144,18 +144,15 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 // Phantom ranks (padding) have rnd = 0 and C_k = 0: no test is true.
 // The argument needs 0 < rnd < C_{K-1}, true whenever C_{K-1} is a normal number
 // (u is in [2^-33, 1 - 2^-33]); a read whose weights all but underflow
-// (C_{K-1} < 1e-290) sends the whole pass to the literal rule below (MODE 3).
+// (C_{K-1} < 1e-290) sends the whole pass to reassign_literal below.
 //   MODE 0: counts only.  MODE 1: + read score of the chosen isoform
 //   (miso_paired.c:157-163), needed when the next iteration records.
-//   MODE 2: + write the chosen isoform per rank (final assignment, chain 0).
-//   MODE 3: literal per-read rule with validity tests (degenerate weights).
 template <int K, int MODE, bool SMEM>
 __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes,
                                               uint32_t ptab_s, const double (&psi)[K],
                                               unsigned long long n_u, int R2, uint32_t gene,
-                                              uint32_t chain, PhiloxKey key, int paired,
-                                              const int *__restrict__ L, int (&cnt)[K], double &rp,
-                                              uint8_t *__restrict__ ass_out) {
+                                              uint32_t chain, const PhiloxKey &key, int paired,
+                                              const int *__restrict__ L, int (&cnt)[K], double &rp) {
   using TM = TileMem<SMEM>;
   const int lane = threadIdx.x & 31;
   const int o = (int) (n_u & 3ull);
@@ -172,7 +169,7 @@ __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t row
   for (int s = 0; s < nsteps; s++) {
     const int T = lane + 32 * s;
     uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key.k0, key.k1, x);
+    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
     uint32_t cw[K + 1];
 #pragma unroll
     for (int k = 0; k <= K; k++) {
@@ -192,72 +189,120 @@ __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t row
         C[k] = S;
       }
       const double rnd = uniform_from_word(x[i]) * S;          // miso.c:70,76
-      if (MODE != 3) {
-        // two compatible isoforms: compare with nextup(rnd), see above
-        const double rc = __longlong_as_double(__double_as_longlong(rnd) + (long long) (flag == 1u));
-        // S this small: u*S may round to 0 or to S itself -- outside the argument above
-        if (flag != 0u && !(S >= 1e-290)) degenerate = true;
-        int chosen = 0;
+      // two compatible isoforms: compare with nextup(rnd), see above
+      const double rc = __longlong_as_double(__double_as_longlong(rnd) + (long long) (flag == 1u));
+      // S this small: u*S may round to 0 or to S itself -- outside the argument above
+      if (flag != 0u && !(S >= 1e-290)) degenerate = true;
+      int chosen = 0;
 #pragma unroll
-        for (int k = 0; k < K - 1; k++) {
-          const bool go_on = rc > C[k];
-          G[k] += go_on;
-          if (MODE != 0) chosen += go_on;
-        }
-        if (MODE == 1 || MODE == 2) {
-          const int rank = 4 * T - o + i;
-          const bool real = rank >= 0 && rank < R2;
-          if (MODE == 1 && real && paired) {
-            uint32_t cc = code[0];
+      for (int k = 0; k < K - 1; k++) {
+        const bool go_on = rc > C[k];
+        G[k] += go_on;
+        if (MODE == 1) chosen += go_on;
+      }
+      if (MODE == 1) {
+        const int rank = 4 * T - o + i;
+        if (rank >= 0 && rank < R2 && paired) {
+          uint32_t cc = code[0];
 #pragma unroll
-            for (int k = 1; k < K; k++)
-              if (chosen == k) cc = code[k];
-            const int Lc = __ldg(L + chosen);
-            const double lp = (double) (Lc - ((int) cc - 1));
-            rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
-          }
-          if (MODE == 2 && real) ass_out[rank] = (uint8_t) chosen;
-        }
-      } else {
-        const bool two = flag == 1u;
-        int chosen = -1;
-        uint32_t cc = 0;
-#pragma unroll
-        for (int k = K - 1; k >= 0; k--) {
-          const bool valid = code[k] != 0u;
-          const bool hit = two ? (rnd < C[k]) : (rnd <= C[k]);
-          if (valid && (hit || chosen < 0)) { chosen = k; cc = code[k]; }
-        }
-#pragma unroll
-        for (int k = 0; k < K; k++) G[k] += (chosen == k);
-        if (chosen >= 0 && paired) {
+          for (int k = 1; k < K; k++)
+            if (chosen == k) cc = code[k];
           const int Lc = __ldg(L + chosen);
           const double lp = (double) (Lc - ((int) cc - 1));
-          rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);
+          rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
         }
-        const int rank = 4 * T - o + i;
-        if (ass_out && rank >= 0 && rank < R2) ass_out[rank] = (uint8_t) chosen;
       }
     }
   }
-  if (MODE != 3) {
-    if (__any_sync(0xffffffffu, degenerate)) return false;
+  if (__any_sync(0xffffffffu, degenerate)) return false;
 #pragma unroll
-    for (int k = 0; k < K - 1; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]);
-    cnt[0] = R2 - G[0];
+  for (int k = 0; k < K - 1; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]);
+  cnt[0] = R2 - G[0];
 #pragma unroll
-    for (int k = 1; k < K - 1; k++) cnt[k] = G[k - 1] - G[k];
-    cnt[K - 1] = G[K - 2];
-  } else {
-#pragma unroll
-    for (int k = 0; k < K; k++) cnt[k] = __reduce_add_sync(0xffffffffu, G[k]);
-  }
-  if (MODE == 1 || MODE == 3) {
+  for (int k = 1; k < K - 1; k++) cnt[k] = G[k - 1] - G[k];
+  cnt[K - 1] = G[K - 2];
+  if (MODE == 1) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
     rp = rp_lane;
   }
   return true;
+}
+
+// The literal rule of miso.c:59-83, read by read, with the compatibility tests
+// spelled out.  Used for the final pass of chain 0 (which has to emit the
+// per-read assignment, miso.c:943-946) and for passes the fast rule declined.
+// Not inlined and not unrolled over reads: it runs once or twice per chain.
+// psi_k is lane k's psi; returns lane k's count in cnt_k and the read score.
+template <int K, bool SMEM>
+__device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t rows, int row_bytes,
+                                              uint32_t ptab_s, double psi_k, unsigned long long n_u,
+                                              int R2, uint32_t gene, uint32_t chain, const PhiloxKey &key,
+                                              int paired, const int *__restrict__ L, int *cnt_k,
+                                              double *rp, uint8_t *__restrict__ ass_out) {
+  using TM = TileMem<SMEM>;
+  const int lane = threadIdx.x & 31;
+  const int o = (int) (n_u & 3ull);
+  const uint32_t Q0 = (uint32_t) (n_u >> 2);
+  const int nsteps = (R2 + o + 127) >> 7;
+  double psi[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) psi[k] = shfl_d(psi_k, k);
+  int n[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) n[k] = 0;
+  double rp_lane = 0.0;
+  for (int s = 0; s < nsteps; s++) {
+    const int T = lane + 32 * s;
+    uint32_t x[4];
+    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      const int rank = 4 * T - o + i;
+      if (rank < 0 || rank >= R2) continue;
+      const int byte = kTilePadFront + rank;
+      auto code_at = [&](int k) -> uint32_t {
+        const uint32_t w = TM::ld(rows + k * row_bytes + (byte & ~3));
+        return (w >> (8 * (byte & 3))) & 0xffu;
+      };
+      const bool two = code_at(K) == 1u;
+      const uint32_t xi = i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3];
+      double S = 0.0, C[K];
+      uint32_t code[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        code[k] = code_at(k);
+        S = S + psi[k] * lds_f64(ptab_s + code[k] * 8u);
+        C[k] = S;
+      }
+      const double rnd = uniform_from_word(xi) * S;
+      int chosen = -1;
+      uint32_t cc = 0;
+#pragma unroll
+      for (int k = K - 1; k >= 0; k--) {
+        const bool valid = code[k] != 0u;
+        const bool hit = two ? (rnd < C[k]) : (rnd <= C[k]);     // miso.c:71 / :78
+        if (valid && (hit || chosen < 0)) { chosen = k; cc = code[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++) n[k] += (chosen == k);
+      if (chosen >= 0 && paired) {
+        const double lp = (double) (__ldg(L + chosen) - ((int) cc - 1));
+        rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);
+      }
+      if (ass_out) ass_out[rank] = (uint8_t) chosen;
+    }
+  }
+  int mine = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int t = __reduce_add_sync(0xffffffffu, n[k]);
+    if (lane == k) mine = t;
+  }
+  *cnt_k = mine;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
+  *rp = rp_lane;
 }
 
 // Everything derived from a candidate alpha (lane i < K-1 holds alpha_i).
@@ -346,7 +391,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   const double sigma = d.sigma, sd = d.sd, covar = d.covar_const;
   const int R2 = d.R2, row_bytes = d.row_bytes, paired = d.paired;
   const uint32_t gid = d.gene_id;
-  const PhiloxKey key = P.key;
+  const PhiloxKey &key = P.key;
   const int *L = d.L;
 
   unsigned long long n_u = 0;
@@ -383,28 +428,30 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   uint8_t *ass_out = (chain == 0) ? P.drawn + d.drawn_off : nullptr;
 
   auto do_pass = [&](int m_next) {
-#pragma unroll
-    for (int k = 0; k < K; k++) psi_r[k] = shfl_d(cur.psi, k);
     const bool last = (m_next >= P.n_iters);
     const bool rec_next = d.rp_always || (paired && m_next >= P.burn_in && lagc == P.lag - 1);
-    bool ok;
-    if (last && ass_out)
-      ok = reassign_pass<K, 2, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
-                                     paired, L, cnt, rp_drawn, ass_out);
-    else if (rec_next && !last)
-      ok = reassign_pass<K, 1, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
-                                     paired, L, cnt, rp_drawn, ass_out);
-    else
-      ok = reassign_pass<K, 0, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
-                                     paired, L, cnt, rp_drawn, ass_out);
-    if (!ok)   // some read's weights all underflowed: redo the pass with the literal rule
-      reassign_pass<K, 3, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired,
-                                L, cnt, rp_drawn, last ? ass_out : nullptr);
-    n_u += (unsigned long long) R2;
-    int c = 0;
+    bool ok = false;
+    if (!(last && ass_out)) {
 #pragma unroll
-    for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
-    cnt_k = c + nfix_k;
+      for (int k = 0; k < K; k++) psi_r[k] = shfl_d(cur.psi, k);
+      if (rec_next && !last)
+        ok = reassign_pass<K, 1, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
+                                       paired, L, cnt, rp_drawn);
+      else
+        ok = reassign_pass<K, 0, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
+                                       paired, L, cnt, rp_drawn);
+      int c = 0;
+#pragma unroll
+      for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
+      cnt_k = c + nfix_k;
+    }
+    if (!ok) {   // final pass of chain 0, or a read whose weights underflow: literal rule
+      int c = 0;
+      reassign_literal<K, SMEM>(rows, row_bytes, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired,
+                                L, &c, &rp_drawn, last ? ass_out : nullptr);
+      cnt_k = c + nfix_k;
+    }
+    n_u += (unsigned long long) R2;
     return rec_next || !ok;
   };
 
@@ -475,8 +522,8 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   }
 }
 
-template <int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(const ChainParams P) {
+template <int K, int WARPS, bool SMEM>
+__global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // layout: [ptab | per-warp {mbarrier(16 B), tile slot}]
@@ -487,7 +534,7 @@ __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(con
   unsigned char *slot = wbase + 16;
 
   for (int i = threadIdx.x; i < P.n_ptab; i += WARPS * 32) s_ptab[i] = P.ptab[i];
-  if (lane == 0 && P.slot_bytes) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (lane == 0 && SMEM) { mbar_init(bar, 1); fence_mbar_init(); }
   __syncthreads();
 
   const int n_items = P.n_genes * P.n_chains;
@@ -501,7 +548,7 @@ __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(con
     const int chain = (int) (item % P.n_chains);
     const GeneDesc &d = P.desc[gi];
     const uint32_t tile_bytes = (uint32_t) d.row_bytes * (K + 1);
-    if (P.slot_bytes) {
+    if (SMEM) {
       __syncwarp();
       if (lane == 0) {
         fence_proxy_async();

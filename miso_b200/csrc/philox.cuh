@@ -19,18 +19,33 @@ namespace misob200 {
 #define MISOB200_PHILOX_W0 0x9E3779B9u
 #define MISOB200_PHILOX_W1 0xBB67AE85u
 
-struct PhiloxKey { uint32_t k0, k1; };
+// The ten round keys (k0 + r*W0, k1 + r*W1) are the same for every draw of a
+// run (the key is the seed), so the host expands them once and they travel in
+// the kernel parameter block: on the device they are constant-bank operands of
+// the round's XOR, not instructions.
+struct PhiloxKey { uint32_t k0[10], k1[10]; };
+
+inline PhiloxKey philox_expand_key(uint64_t seed) {
+  PhiloxKey k;
+  uint32_t a = (uint32_t) seed, b = (uint32_t) (seed >> 32);
+  for (int r = 0; r < 10; r++) {
+    k.k0[r] = a; k.k1[r] = b;
+    a += MISOB200_PHILOX_W0; b += MISOB200_PHILOX_W1;
+  }
+  return k;
+}
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+                                              const PhiloxKey &key, uint32_t (&out)[4]) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
-    const uint32_t hi0 = __umulhi(MISOB200_PHILOX_M0, c0), lo0 = MISOB200_PHILOX_M0 * c0;
-    const uint32_t hi1 = __umulhi(MISOB200_PHILOX_M1, c2), lo1 = MISOB200_PHILOX_M1 * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += MISOB200_PHILOX_W0; k1 += MISOB200_PHILOX_W1;
+    const unsigned long long p0 = (unsigned long long) MISOB200_PHILOX_M0 * c0;   // IMAD.WIDE.U32
+    const unsigned long long p1 = (unsigned long long) MISOB200_PHILOX_M1 * c2;
+    const uint32_t n0 = (uint32_t) (p1 >> 32) ^ c1 ^ key.k0[r];
+    const uint32_t n2 = (uint32_t) (p0 >> 32) ^ c3 ^ key.k1[r];
+    c1 = (uint32_t) p1; c3 = (uint32_t) p0;
+    c0 = n0; c2 = n2;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
@@ -41,18 +56,18 @@ __device__ __forceinline__ double uniform_from_word(uint32_t w) {
 }
 
 __device__ __forceinline__ double stream_uniform(unsigned long long n, uint32_t gene, uint32_t chain,
-                                                 PhiloxKey key) {
+                                                 const PhiloxKey &key) {
   uint32_t x[4];
-  philox4x32_10((uint32_t) (n >> 2), 0u, gene, chain, key.k0, key.k1, x);
+  philox4x32_10((uint32_t) (n >> 2), 0u, gene, chain, key, x);
   const uint32_t sel = (uint32_t) n & 3u;
   const uint32_t w = sel == 0 ? x[0] : sel == 1 ? x[1] : sel == 2 ? x[2] : x[3];
   return uniform_from_word(w);
 }
 
 __device__ __forceinline__ double stream_normal(uint32_t n, uint32_t gene, uint32_t chain,
-                                                PhiloxKey key) {
+                                                const PhiloxKey &key) {
   uint32_t x[4];
-  philox4x32_10(n, 1u, gene, chain, key.k0, key.k1, x);
+  philox4x32_10(n, 1u, gene, chain, key, x);
   const unsigned long long a = ((unsigned long long) x[0] << 21) | (x[1] >> 11);
   const unsigned long long b = ((unsigned long long) x[2] << 21) | (x[3] >> 11);
   const double u1 = (double) (a + 1ull) * 0x1p-53;

@@ -253,7 +253,7 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   size_t smem = (size_t) ptab_bytes + WARPS * (16 + (size_t) slot);
   const size_t smem_cap = 227 * 1024;
   if (smem > smem_cap) { slot = 0; smem = (size_t) ptab_bytes + WARPS * 16; }   // stream tiles through L2
-  auto kern = chain_kernel<K, WARPS>;
+  auto kern = slot ? chain_kernel<K, WARPS, true> : chain_kernel<K, WARPS, false>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -277,7 +277,7 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   P.queue = st->d_queue + K;
   P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
   P.start = st->params.start;
-  P.key.k0 = (uint32_t) st->params.seed; P.key.k1 = (uint32_t) (st->params.seed >> 32);
+  P.key = philox_expand_key(st->params.seed);
   P.slot_bytes = slot;
   kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[K]>>>(P);
   CK(cudaGetLastError());
