@@ -5,6 +5,7 @@
 // persistent warps through an atomic counter, longest first.  Buckets run on
 // separate streams so the tail of one overlaps the head of the next.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -388,11 +389,13 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
 
 // ---- posterior summaries --------------------------------------------------
 // One CTA per gene: mean over the C*S recorded samples and the 95% credible
-// interval by order statistics, indices int(round(0.025 n)) - 1 and
-// int(round(0.975 n)) - 1 of the sorted samples with Python-2 rounding (half
-// away from zero) -- /root/reference/misopy/credible_intervals.py:31-55 --
+// interval by order statistics -- /root/reference/misopy/credible_intervals.py:31-55:
+// alpha = 1 - 0.95, indices int(round((alpha/2) n)) - 1 and
+// int(round((1 - alpha/2) n)) - 1 of the sorted samples, where `round` is
+// numpy's (the module does `from numpy import *`), i.e. half-to-even on the
+// fp64 product; the host computes the two indices with the same expression --
 // plus the per-isoform assigned-read counts of chain 0.
-__global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, int S,
+__global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, int S, int lo, int hi,
                                const double *samples, const uint8_t *drawn, const int *accrej,
                                double *summary) {
   extern __shared__ double vals[];
@@ -416,7 +419,6 @@ __global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, 
     const int a = drawn[d.drawn_off + i];
     if (a < K) atomicAdd(&s_cnt[a], 1);
   }
-  const int lo = (int) floor(0.025 * n + 0.5) - 1, hi = (int) floor(0.975 * n + 0.5) - 1;
   for (int k = 0; k < kMaxIso; k++) {
     double mean = 0.0, vlo = 0.0, vhi = 0.0;
     if (k < K && n > 0) {
@@ -477,8 +479,10 @@ int summarize(Plan &plan, double *summary) {
   const size_t smem = std::max(n, 1) * sizeof(double);
   if (smem > 200 * 1024) { set_error("summarize: too many samples per gene for the on-chip selection"); return MISOB200_UNIMPLEMENTED; }
   CK(cudaFuncSetAttribute(summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, S, st->d_samples, st->d_drawn,
-                                              st->d_accrej, st->d_summary);
+  const double alpha = 1 - 0.95;
+  const int lo = (int) nearbyint((alpha / 2) * n) - 1, hi = (int) nearbyint((1 - alpha / 2) * n) - 1;
+  summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, S, lo, hi, st->d_samples,
+                                              st->d_drawn, st->d_accrej, st->d_summary);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(summary, st->d_summary, (size_t) G * MISOB200_SUMMARY_F64 * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
   CK(cudaStreamSynchronize(st->stream));

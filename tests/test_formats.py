@@ -1,0 +1,55 @@
+"""`.miso` writer / parser / credible intervals (miso_b200/miso_format.py) --
+the on-disk contract of misopy/miso_sampler.py:376-466 and
+misopy/credible_intervals.py:4-55."""
+import numpy as np
+
+from miso_b200 import miso_format as mf
+
+
+def test_header_and_body_format(tmp_path):
+    rng = np.random.default_rng(0)
+    psi = rng.dirichlet(np.ones(2), size=30)
+    sc = -1000 - rng.random(30) * 10
+    ass = np.array([0, 0, 1, -1, 1, 1, 0])
+    h = mf.format_header([["A", "B", "C"], ["A", "C"]], [("A", 183), ("B", 154), ("C", 3336)], 5000, 500, 10,
+                         23.456, "drift", [(0.0, 1.0), (1.0, 0.0), (1.0, 1.0)], [5.0, 7.0, 700.0], ass, "chr10",
+                         "+", [98481349, 98481349], [98488777, 98488777])
+    assert h.startswith("#isoforms=['A_B_C','A_C']\texon_lens=('A',183),('B',154),('C',3336)\titers=5000\t"
+                        "burn_in=500\tlag=10\tpercent_accept=23.46\tproposal_type=drift\t"
+                        "counts=(0,1):5,(1,0):7,(1,1):700\tassigned_counts=0:3,1:3\tchrom=chr10\tstrand=+\t")
+    assert h.endswith("mRNA_starts=98481349,98481349\tmRNA_ends=98488777,98488777\n")
+    path = str(tmp_path / "ev.miso")
+    mf.write_miso(path, h, psi, sc)
+    lines = open(path).read().splitlines()
+    assert lines[1] == "sampled_psi\tlog_score" and len(lines) == 32
+    assert lines[2] == "%.4f,%.4f\t%.2f" % (psi[0, 0], psi[0, 1], sc[0])
+    samples, header, scores, smap, smap_score, counts = mf.load_samples(path)
+    np.testing.assert_allclose(samples, np.round(psi, 4), atol=1e-12)
+    np.testing.assert_allclose(scores, np.round(sc, 2), atol=1e-9)
+    assert header["iters"] == "5000" and counts == "(0,1):5,(1,0):7,(1,1):700"
+    assert smap == [float(v) for v in max(ln.split("\t")[0] for ln in lines[2:]).split(",")]
+
+
+def test_header_without_chrom():
+    h = mf.format_header(["iso1", "iso2"], [("e", 10)], 10, 1, 1, 50.0, "drift", [], [], np.array([-1, -1]))
+    assert "chrom=NA\tstrand=NA" in h and "assigned_counts=\t" in h
+
+
+def test_credible_interval_indices_follow_numpy_round():
+    # credible_intervals.py:45-49 with `from numpy import *`: half-to-even on the fp64 product
+    for n in (20, 60, 100, 450, 900, 2700, 1001):
+        alpha = 1 - 0.95
+        lo, hi = mf.credible_interval_indices(n)
+        assert lo == int(np.round((alpha / 2) * n)) - 1 and hi == int(np.round((1 - alpha / 2) * n)) - 1
+    s = np.linspace(0, 1, 2700)[::-1].copy()
+    lo, hi = mf.compute_credible_intervals(np.stack([s, 1 - s], axis=1))
+    assert (lo, hi) == (np.sort(s)[67], np.sort(s)[2631])      # 0.025*2700 = 67.5(+eps) -> 68
+    out = mf.format_credible_intervals("ev", np.stack([s, 1 - s], axis=1))
+    assert out[0] == "ev" and out[1] == "0.50"
+    out3 = mf.format_credible_intervals("ev", np.random.default_rng(1).dirichlet(np.ones(3), size=500))
+    assert len(out3) == 4 and out3[1].count(",") == 2
+
+
+def test_count_isoform_assignments():
+    assert mf.count_isoform_assignments(np.array([0, 2, 2, -1])) == [(0, 1), (1, 0), (2, 2)]
+    assert mf.count_isoform_assignments(np.array([-1, -1])) == []   # range(max+1) is empty, reads_utils.py:42-45

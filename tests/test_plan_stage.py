@@ -1,0 +1,106 @@
+"""Host setup stage of the product (miso_b200/csrc/plan.cpp, through the C ABI)
+against the oracle: compatibility codes, the draw order (ties included -- it
+decides which read gets which uniform), read classes, the insert-length table.
+Integer / index work: bit-exact.  No GPU needed."""
+import numpy as np
+import pytest
+
+import miso_b200 as mb
+from golden_util import load_cases
+
+CASES = load_cases()
+
+
+def plan_of(case):
+    g = mb.Gene(case.exons, case.isoforms)
+    rb = mb.ReadBatch([g], [case.pos], [case.cig], case.read_len, case.overhang, bool(case.paired), *case.pe)
+    return mb.Plan(keep_match=True).append(rb)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+def test_setup_matches_oracle_on_golden_inputs(port, case):
+    plan = plan_of(case)
+    K, R, R2, ncls, status = plan.info()[0]
+    assert status == 0 and K == len(case.isoforms)
+    codes, order = plan.match(0)
+    if case.paired:
+        want = port.match_pe(case.exons, case.isoforms, case.pos, case.cig, case.read_len, *case.pe, case.overhang)
+        fp, fs = plan.fragment_table()
+        wfp, wfs = port.fragment_table(case.pe[0], case.pe[1], case.pe[2], case.read_len)
+        np.testing.assert_array_equal(fp, wfp)
+        assert fs == wfs
+        np.testing.assert_array_equal(np.where(codes > 0, codes - 1 + fs, -1), want["fraglen"])
+        np.testing.assert_array_equal(np.where(codes > 0, fp[np.maximum(codes - 1, 0)], 0.0), want["match"])
+        ct, cc = want["bin_class_templates"], want["bin_class_counts"]
+    else:
+        want = port.match_se(case.exons, case.isoforms, case.pos, case.cig, case.read_len, case.overhang)
+        np.testing.assert_array_equal(codes.astype(float), want["match"])
+        ct, cc = want["class_templates"], want["class_counts"]
+    np.testing.assert_array_equal(order, want["order"])
+    t, c = plan.classes(0)
+    np.testing.assert_array_equal(t, ct.T)
+    np.testing.assert_array_equal(c, cc)
+    # reads that draw = reads with >= 2 compatible isoforms (miso.c:65-68)
+    assert R2 == int(((codes != 0).sum(axis=0) >= 2).sum())
+    # golden class tables too (they came from the unmodified reference)
+    np.testing.assert_array_equal(t, case.class_templates.T)
+    np.testing.assert_array_equal(c, case.class_counts)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_setup_matches_oracle_on_synthetic_workload(port, kind):
+    w = mb.Workload(kind, 10, 250, 36, 250.0, 900.0, 4.0, seed=3)
+    plan = mb.Plan(keep_match=True).append(w)
+    for g in range(10):
+        ex, iso, pos, cig = w.gene(g)
+        codes, order = plan.match(g)
+        if kind:
+            want = port.match_pe(ex, iso, pos, cig, 36, 250.0, 900.0, 4.0)
+            _, fs = plan.fragment_table()
+            np.testing.assert_array_equal(np.where(codes > 0, codes - 1 + fs, -1), want["fraglen"])
+        else:
+            want = port.match_se(ex, iso, pos, cig, 36)
+            np.testing.assert_array_equal(codes.astype(float), want["match"])
+        np.testing.assert_array_equal(order, want["order"])
+
+
+def test_edge_cases_and_status_codes():
+    g3 = mb.Gene(((1, 100), (201, 300), (401, 500)), ((0, 1), (0, 2), (0, 1, 2)))
+    # empty read set: a valid plan entry with nothing to draw
+    p = mb.Plan().append(mb.ReadBatch([g3], [[]], [[]], 33))
+    assert p.info()[0].tolist() == [3, 0, 0, 0, 0]
+    # bad CIGAR -> EINVAL for that gene only (solve.c:295-298 aborts the call in the reference)
+    p = mb.Plan().append(mb.ReadBatch([g3, g3], [[10], [10]], [["33Q"], ["33M"]], 33))
+    assert p.info()[:, 4].tolist() == [4, 0]
+    # S/H inside the alignment (solve.c:244-247)
+    p = mb.Plan().append(mb.ReadBatch([g3], [[10]], [["10M2S21M"]], 33))
+    assert p.info()[0, 4] == 4
+    # one isoform: rejected; nine isoforms: not implemented on chip
+    g1 = mb.Gene(((1, 100),), ((0,),))
+    assert mb.Plan().append(mb.ReadBatch([g1], [[1]], [["33M"]], 33)).info()[0, 4] == 4
+    ex9 = tuple((1 + 200 * i, 100 + 200 * i) for i in range(10))
+    g9 = mb.Gene(ex9, tuple((0, i + 1) for i in range(9)))
+    assert mb.Plan().append(mb.ReadBatch([g9], [[1]], [["33M"]], 33)).info()[0, 4] == 12
+    # overhang >= read_len / 2 (miso.c:691-694)
+    assert mb.Plan().append(mb.ReadBatch([g3], [[1]], [["33M"]], 33, overhang=16)).info()[0, 4] == 4
+    # one plan = one library
+    p = mb.Plan().append(mb.ReadBatch([g3], [[1]], [["33M"]], 33))
+    with pytest.raises(mb.InternalError):
+        p.append(mb.ReadBatch([g3], [[1]], [["36M"]], 36))
+    # odd trailing mate of a paired batch is ignored (solve.c:187)
+    p = mb.Plan().append(mb.ReadBatch([g3], [[10, 60, 20]], [["33M"] * 3], 33, paired=True, frag_mean=80.0,
+                                      frag_var=100.0, num_devs=4.0))
+    assert p.info()[0, 1] == 1
+
+
+def test_tile_layout_and_sizes():
+    w = mb.Workload(1, 6, 500, 36, 250.0, 900.0, 4.0, seed=9)
+    plan = mb.Plan().append(w)
+    G, n_reads, tile_bytes = plan.size()
+    info = plan.info()
+    assert G == 6 and n_reads == 6 * 500
+    want = sum(((int(r2) + 3 + 127) // 128 * 128 + 16) * (int(k) + 1) for k, _, r2, _, _ in info)
+    assert tile_bytes == want and tile_bytes % 16 == 0
+    p = mb.make_params(1000, 100, 9, 3)
+    ns, nl, na = plan.output_sizes(p)
+    assert nl == 6 * 3 * 100 and na == n_reads and ns == int((info[:, 0] * 300).sum())
