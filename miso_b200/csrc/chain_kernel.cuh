@@ -42,6 +42,7 @@ struct ChainParams {
   const uint8_t *tiles;
   const double *ptab;
   int n_ptab;
+  double ptab_min;           // smallest non-zero entry of ptab
   double *samples;
   double *loglik;
   uint8_t *drawn;            // final chain-0 assignment of the reads that draw, draw order
@@ -143,12 +144,14 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 // ratio needs are n_0 = R2 - G_0, n_k = G_{k-1} - G_k, n_{K-1} = G_{K-2}.
 // Phantom ranks (padding) have rnd = 0 and C_k = 0: no test is true.
 // The argument needs 0 < rnd < C_{K-1}, true whenever C_{K-1} is a normal number
-// (u is in [2^-33, 1 - 2^-33]); a read whose weights all but underflow
-// (C_{K-1} < 1e-290) sends the whole pass to reassign_literal below.
+// (u is in [2^-33, 1 - 2^-33]).  Every drawing read has a compatible isoform, so
+// C_{K-1} >= min_k psi_k * min nonzero ptab: the caller checks that bound once per
+// pass (>= 1e-290, which also rules out a negative psi_{K-1} = 1 - sum) and
+// otherwise runs reassign_literal below instead.
 //   MODE 0: counts only.  MODE 1: + read score of the chosen isoform
 //   (miso_paired.c:157-163), needed when the next iteration records.
 template <int K, int MODE, bool SMEM>
-__device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes,
+__device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes,
                                               uint32_t ptab_s, const double (&psi)[K],
                                               unsigned long long n_u, int R2, uint32_t gene,
                                               uint32_t chain, const PhiloxKey &key, int paired,
@@ -163,7 +166,6 @@ __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t row
 #pragma unroll
   for (int k = 0; k < K; k++) G[k] = 0;
   double rp_lane = 0.0;
-  bool degenerate = false;
   typename TM::addr_t a = rows + 4 * lane;
 
   for (int s = 0; s < nsteps; s++) {
@@ -179,7 +181,8 @@ __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t row
     a += 128;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const uint32_t flag = __byte_perm(cw[K], 0u, 0x4440u | (uint32_t) i);
+      // flag byte: 1 = exactly two compatible isoforms (compare with nextup(rnd)), else 0
+      const uint32_t two = __byte_perm(cw[K], 0u, 0x4440u | (uint32_t) i);
       double S = 0.0, C[K];
       uint32_t code[K];
 #pragma unroll
@@ -189,10 +192,7 @@ __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t row
         C[k] = S;
       }
       const double rnd = uniform_from_word(x[i]) * S;          // miso.c:70,76
-      // two compatible isoforms: compare with nextup(rnd), see above
-      const double rc = __longlong_as_double(__double_as_longlong(rnd) + (long long) (flag == 1u));
-      // S this small: u*S may round to 0 or to S itself -- outside the argument above
-      if (flag != 0u && !(S >= 1e-290)) degenerate = true;
+      const double rc = __longlong_as_double(__double_as_longlong(rnd) + (long long) two);
       int chosen = 0;
 #pragma unroll
       for (int k = 0; k < K - 1; k++) {
@@ -214,7 +214,6 @@ __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t row
       }
     }
   }
-  if (__any_sync(0xffffffffu, degenerate)) return false;
 #pragma unroll
   for (int k = 0; k < K - 1; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]);
   cnt[0] = R2 - G[0];
@@ -226,7 +225,6 @@ __device__ __forceinline__ bool reassign_pass(typename TileMem<SMEM>::addr_t row
     for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
     rp = rp_lane;
   }
-  return true;
 }
 
 // The literal rule of miso.c:59-83, read by read, with the compatibility tests
@@ -432,14 +430,22 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     const bool rec_next = d.rp_always || (paired && m_next >= P.burn_in && lagc == P.lag - 1);
     bool ok = false;
     if (!(last && ass_out)) {
+      double pmin = 1.0;
 #pragma unroll
-      for (int k = 0; k < K; k++) psi_r[k] = shfl_d(cur.psi, k);
+      for (int k = 0; k < K; k++) {
+        psi_r[k] = shfl_d(cur.psi, k);
+        pmin = psi_r[k] < pmin ? psi_r[k] : pmin;       // a NaN psi never lowers pmin ...
+        ok = ok || !(psi_r[k] == psi_r[k]);             // ... so flag it here
+      }
+      ok = !ok && (pmin * P.ptab_min >= 1e-290);        // fast rule valid for every read of this pass
+    }
+    if (ok) {
       if (rec_next && !last)
-        ok = reassign_pass<K, 1, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
-                                       paired, L, cnt, rp_drawn);
+        reassign_pass<K, 1, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+                                  cnt, rp_drawn);
       else
-        ok = reassign_pass<K, 0, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key,
-                                       paired, L, cnt, rp_drawn);
+        reassign_pass<K, 0, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+                                  cnt, rp_drawn);
       int c = 0;
 #pragma unroll
       for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;

@@ -52,7 +52,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 // (w + 0.5) * 2^-32, exact in fp64
 __device__ __forceinline__ double uniform_from_word(uint32_t w) {
-  return (double) w * 0x1p-32 + 0x1p-33;
+  return __fma_rn((double) w, 0x1p-32, 0x1p-33);   // one instruction; exact either way
 }
 
 __device__ __forceinline__ double stream_uniform(unsigned long long n, uint32_t gene, uint32_t chain,

@@ -340,7 +340,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
       out.tile[(size_t) k * row_bytes + kTilePadFront + i] = (uint8_t) col[k];
       nv += col[k] != 0;
     }
-    out.tile[(size_t) K * row_bytes + kTilePadFront + i] = (nv == 2) ? 1 : 2;
+    out.tile[(size_t) K * row_bytes + kTilePadFront + i] = (nv == 2) ? 1 : 0;   // flag row, see chain_kernel.cuh
   }
   if (plan.keep_match) { h.codes = std::move(codes); h.order = std::move(order); }
 }

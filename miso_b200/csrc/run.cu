@@ -271,6 +271,8 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   P.tiles = st->d_tiles;
   P.ptab = st->d_ptab;
   P.n_ptab = (int) plan.ptab.size();
+  P.ptab_min = 1.0;
+  for (double v : plan.ptab) if (v > 0 && v < P.ptab_min) P.ptab_min = v;
   P.samples = st->d_samples;
   P.loglik = st->d_loglik;
   P.drawn = st->d_drawn;
