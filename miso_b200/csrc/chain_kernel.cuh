@@ -32,7 +32,13 @@
 #include "philox.cuh"
 #include "plan.hpp"
 
+#ifndef MISOB200_READ_UNROLL
+#define MISOB200_READ_UNROLL 2   /* measured: 2 beats 4 (I-cache) and 1 (ILP), profiles/README.md */
+#endif
+
 namespace misob200 {
+
+constexpr int kReadUnroll = MISOB200_READ_UNROLL;   // reads of a lane's step unrolled together
 
 struct ChainParams {
   const GeneDesc *desc;
@@ -179,7 +185,7 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
       cw[k] = __byte_perm(w0, w1, sel);
     }
     a += 128;
-#pragma unroll
+#pragma unroll (kReadUnroll)
     for (int i = 0; i < 4; i++) {
       // flag byte: 1 = exactly two compatible isoforms (compare with nextup(rnd)), else 0
       const uint32_t two = __byte_perm(cw[K], 0u, 0x4440u | (uint32_t) i);
@@ -191,7 +197,7 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
         S = S + psi[k] * lds_f64(ptab_s + code[k] * 8u);     // CUMSUM, miso_paired.c:11-22
         C[k] = S;
       }
-      const double rnd = uniform_from_word(x[i]) * S;          // miso.c:70,76
+      const double rnd = uniform_from_word(MISOB200_READ_UNROLL == 4 ? x[i] : (i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3])) * S;          // miso.c:70,76
       const double rc = __longlong_as_double(__double_as_longlong(rnd) + (long long) two);
       int chosen = 0;
 #pragma unroll
@@ -403,8 +409,8 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   }
 
   // normals are produced 32 at a time (lane l holds normal zbase + l)
-  uint32_t zbase = 0;
-  double zbuf = stream_normal((uint32_t) lane, gid, (uint32_t) chain, key);
+  uint32_t zbase = 0xffffff00u;           // forces a refill on first use
+  double zbuf = 0.0;
   auto next_normals = [&](uint32_t first) -> double {   // lane i < len gets normal first + i
     if (first - zbase + (uint32_t) len > 32u) {
       zbase = first;
@@ -413,10 +419,8 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     return shfl_d(zbuf, (int) ((first - zbase + (uint32_t) lane) & 31u));
   };
 
-  // first proposal is adopted unconditionally (miso.c:834)
-  alpha = alpha + sd * next_normals(0u);
-  Derived cur = derive<K>(alpha, offset_k, hyper_m1_k, lg_sum, lg_each);
-
+  Derived cur;
+  cur.psi = cur.lp = cur.q = cur.dir = cur.prod = 0.0;
   double psi_r[K];
   int cnt[K];
   int cnt_k;               // lane k: reads currently assigned to isoform k
@@ -461,13 +465,17 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     return rec_next || !ok;
   };
 
-  bool have_rp = do_pass(0);     // initial assignment (miso.c:840-843)
+  bool have_rp = false;
 
-  for (int m = 0; m < P.n_iters; m++) {
+  // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed
+  // by the initial assignment (miso.c:840-843); m >= 0 are the iterations proper.
+  for (int m = -1; m < P.n_iters; m++) {
     // ---- propose (miso.c:851) --------------------------------------------
     const double alphaN = alpha + sd * next_normals((uint32_t) (m + 1) * (uint32_t) len);
     const Derived nw = derive<K>(alphaN, offset_k, hyper_m1_k, lg_sum, lg_each);
-
+    if (m < 0) {
+      alpha = alphaN; cur = nw;
+    } else {
     // ---- joint scores (miso.c:524-529) -----------------------------------
     double rp;
     if (!paired) rp = count_dot<K>(cnt_k, rs_se_k);          // sum_r isoscores[ass_r], miso.c:267-271
@@ -518,7 +526,8 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
       }
     }
 
-    // ---- reassign (miso.c:895-898) -----------------------------------------
+    }
+    // ---- reassign (miso.c:895-898; for m == -1 the initial assignment) ---------
     have_rp = do_pass(m + 1);
   }
 
