@@ -187,6 +187,14 @@ int misob200_transfer_bytes(misob200_plan_t *plan, int64_t *h2d, int64_t *d2h);
 #define MISOB200_SUMMARY_F64 32
 int misob200_summarize(misob200_plan_t *plan, double *summary);
 
+/* Two-sample comparison on the device (misopy/hypothesis_test.py:89-179,348-380;
+   compare_miso --compare-samples): both plans hold the same events in the same
+   order, have run with the same iterations/burn-in/lag/chains and are resident
+   on the same GPU.  out: n_genes records of 32 f64 = bayes_factor[8],
+   mean1-mean2 [8], mean|delta| [8], KDE(0) [8]. */
+#define MISOB200_COMPARE_F64 32
+int misob200_compare(misob200_plan_t *plan_a, misob200_plan_t *plan_b, double *out);
+
 /* ---- multi-GPU: genes are sharded by the caller, one process per GPU;
    the only exchange is one all-gather of the summary records ------------- */
 int misob200_comm_unique_id(char *id128);		/* rank 0 */

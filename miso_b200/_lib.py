@@ -72,6 +72,7 @@ def _load():
     lib.misob200_download.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.misob200_release_device.argtypes = [vp]
     lib.misob200_summarize.argtypes = [vp, vp]
+    lib.misob200_compare.argtypes = [vp, vp, vp]
     lib.misob200_bucket_timing.argtypes = [vp, vp]
     lib.misob200_transfer_bytes.argtypes = [vp, vp, vp]
     lib.misob200_comm_unique_id.argtypes = [vp]
@@ -96,7 +97,7 @@ EXPORTS = [
     "misob200_plan_gene_info", "misob200_plan_gene_classes", "misob200_plan_gene_match",
     "misob200_plan_fragment_table", "misob200_plan_offsets", "misob200_plan_output_sizes",
     "misob200_run", "misob200_upload", "misob200_run_resident", "misob200_download",
-    "misob200_release_device", "misob200_summarize", "misob200_bucket_timing",
+    "misob200_release_device", "misob200_summarize", "misob200_bucket_timing", "misob200_compare",
     "misob200_transfer_bytes", "misob200_comm_unique_id",
     "misob200_comm_init", "misob200_comm_allgather", "misob200_comm_barrier_max",
     "misob200_comm_destroy", "misob200_host_alloc", "misob200_host_free",

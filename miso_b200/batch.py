@@ -274,6 +274,14 @@ class Plan:
         check(lib.misob200_summarize(self.h, ptr(s)))
         return s[:G]
 
+    def compare(self, other):
+        """Bayes factors of self (sample 1) vs other (sample 2), [n_genes, 32]:
+        bf[8], mean1 - mean2 [8], mean|delta| [8], KDE(0) [8]."""
+        G = self.size()[0]
+        out = np.zeros((max(G, 1), 32))
+        check(lib.misob200_compare(self.h, other.h, ptr(out)))
+        return out[:G]
+
     def bucket_timing(self):
         ms = np.zeros(9)
         check(lib.misob200_bucket_timing(self.h, ptr(ms)))

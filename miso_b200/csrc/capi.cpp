@@ -20,6 +20,7 @@ int device_count(int *n);
 int bucket_timing(Plan &plan, double *ms);
 long long input_bytes(const Plan &plan);
 long long output_bytes(Plan &plan);
+int compare(Plan &pa, Plan &pb, double *out);
 }  // namespace misob200
 
 using namespace misob200;
@@ -182,6 +183,10 @@ int misob200_transfer_bytes(misob200_plan_t *plan, int64_t *h2d, int64_t *d2h) {
   if (h2d) *h2d = input_bytes(plan->p);
   if (d2h) *d2h = output_bytes(plan->p);
   return 0;
+}
+int misob200_compare(misob200_plan_t *plan_a, misob200_plan_t *plan_b, double *out) {
+  if (!plan_a || !plan_b || !out) return MISOB200_EINVAL;
+  return compare(plan_a->p, plan_b->p, out);
 }
 int misob200_summarize(misob200_plan_t *plan, double *summary) {
   if (!plan || !summary) return MISOB200_EINVAL;

@@ -491,6 +491,95 @@ int summarize(Plan &plan, double *summary) {
   return 0;
 }
 
+// ---- two-sample comparison (misopy/hypothesis_test.py:89-179, :348-380) --------
+// One CTA per event.  For isoform k: delta_i = psi1[i,k] - psi2[i,k] over the n
+// paired posterior samples; if mean|delta| <= 0.009 or all deltas are equal the
+// posterior is taken as peaked on the null (BF = 0); otherwise a Gaussian KDE with
+// bandwidth factor 0.3 (scipy gaussian_kde subclass: covariance = var(delta, ddof=1)
+// * 0.3^2) is evaluated at 0 and BF = 1 / KDE(0), capped at 1e12.
+// out record (32 f64): bf[8], mean1-mean2 [8], mean|delta| [8], KDE(0) [8].
+__global__ void compare_kernel(const GeneDesc *da, const GeneDesc *db, int n_genes, int n,
+                               const double *sa, const double *sb, double *out) {
+  const int g = blockIdx.x;
+  if (g >= n_genes) return;
+  const GeneDesc &a = da[g], &b = db[g];
+  double *o = out + (size_t) g * 32;
+  __shared__ double red[4][32];
+  const int K = a.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  auto block_sum = [&](double v, int slot) -> double {
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __syncthreads();
+    if (lane == 0) red[slot][warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; w++) t += red[slot][w];
+    return t;
+  };
+  for (int k = 0; k < kMaxIso; k++) {
+    double bf = 0.0, dm = 0.0, mabs = 0.0, kde = 0.0;
+    if (k < K && K == b.K && a.status == 0 && b.status == 0 && n > 0) {
+      double s = 0.0, sab = 0.0, same = 1.0;
+      const double d0 = sa[a.sample_off + k] - sb[b.sample_off + k];
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = sa[a.sample_off + (long long) i * K + k] - sb[b.sample_off + (long long) i * K + k];
+        s += d; sab += fabs(d);
+        if (d - d0 != 0.0) same = 0.0;
+      }
+      const double mean = block_sum(s, 0) / n;
+      mabs = block_sum(sab, 1) / n;
+      const bool all_same = block_sum(1.0 - same, 2) == 0.0;
+      dm = mean;
+      if (mabs <= 0.009 || all_same) {
+        bf = 0.0; kde = INFINITY;               // NullPeakedDensity, hypothesis_test.py:15-26
+      } else {
+        double ss = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const double d = sa[a.sample_off + (long long) i * K + k] - sb[b.sample_off + (long long) i * K + k];
+          ss += (d - mean) * (d - mean);
+        }
+        const double var = block_sum(ss, 3) / (n - 1);
+        const double cov = var * 0.3 * 0.3;
+        double e = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const double d = sa[a.sample_off + (long long) i * K + k] - sb[b.sample_off + (long long) i * K + k];
+          e += exp(-0.5 * d * d / cov);
+        }
+        kde = block_sum(e, 0) / (n * sqrt(2.0 * 3.14159265358979323846 * cov));
+        bf = kde == 0.0 ? 1e12 : 1.0 / kde;
+        if (bf > 1e12) bf = 1e12;
+      }
+    }
+    if (threadIdx.x == 0) { o[k] = bf; o[8 + k] = dm; o[16 + k] = mabs; o[24 + k] = kde; }
+    __syncthreads();
+  }
+}
+
+int compare(Plan &pa, Plan &pb, double *out) {
+  DevState *a = static_cast<DevState *>(pa.dev), *b = static_cast<DevState *>(pb.dev);
+  if (!a || !b || !a->have_run || !b->have_run) { set_error("compare: both plans must have run and stay resident"); return MISOB200_EINVAL; }
+  if (a->device != b->device) { set_error("compare: the two samples of an event must live on the same GPU"); return MISOB200_EINVAL; }
+  if (pa.desc.size() != pb.desc.size() || a->params.n_chains != b->params.n_chains || S_of(a->params) != S_of(b->params)) {
+    set_error("compare: plans differ in events or in the number of recorded samples"); return MISOB200_EINVAL;
+  }
+  for (size_t g = 0; g < pa.desc.size(); g++)
+    if (pa.desc[g].K != pb.desc[g].K) {
+      set_error("compare: event " + std::to_string(g) + " has a different number of isoforms in the two samples");
+      return MISOB200_EINVAL;
+    }
+  CK(cudaSetDevice(a->device));
+  const int G = (int) pa.desc.size();
+  if (G == 0) return 0;
+  const int n = a->params.n_chains * S_of(a->params);
+  double *d_out = nullptr;
+  CK(cudaMalloc(&d_out, (size_t) G * 32 * sizeof(double)));
+  compare_kernel<<<G, 128, 0, a->stream>>>(a->d_desc, b->d_desc, G, n, a->d_samples, b->d_samples, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_out, (size_t) G * 32 * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
+  CK(cudaStreamSynchronize(a->stream));
+  cudaFree(d_out);
+  return 0;
+}
+
 void *device_summary_ptr(Plan &plan) {
   DevState *st = static_cast<DevState *>(plan.dev);
   return st ? st->d_summary : nullptr;

@@ -118,3 +118,52 @@ def format_credible_intervals(event_name, samples, confidence_level=0.95):
                 ",".join("%.2f" % c[0] for c in ci), ",".join("%.2f" % c[1] for c in ci)]
     ci = compute_credible_intervals(s, confidence_level)
     return [event_name, "%.2f" % s.mean(axis=0)[0], "%.2f" % ci[0], "%.2f" % ci[1]]
+
+
+# ---- two-sample comparison (compare_miso) -----------------------------------------
+
+BF_HEADER = ["event_name", "sample1_posterior_mean", "sample1_ci_low", "sample1_ci_high",
+             "sample2_posterior_mean", "sample2_ci_low", "sample2_ci_high", "diff", "bayes_factor",
+             "isoforms", "sample1_counts", "sample1_assigned_counts", "sample2_counts",
+             "sample2_assigned_counts", "chrom", "strand", "mRNA_starts", "mRNA_ends"]
+
+
+def bayes_factor(samples1, samples2, smoothing_param=0.3, max_bf=1e12):
+    """Per-isoform Bayes factor of delta psi != 0, as ``compute_delta_densities`` +
+    ``compute_bayes_factor`` (``misopy/hypothesis_test.py:89-179,348-380``): Gaussian KDE of
+    the paired differences with covariance = var(ddof=1) * smoothing_param**2, evaluated
+    at 0; a posterior peaked on the null (mean |delta| <= 0.009 or constant) gives 0."""
+    s1, s2 = np.asarray(samples1, float), np.asarray(samples2, float)
+    out = []
+    for k in range(s1.shape[1]):
+        d = s1[:, k] - s2[:, k]
+        if np.mean(np.abs(d)) <= 0.009 or np.all(d - d[0] == 0):
+            out.append(0.0)
+            continue
+        cov = np.var(d, ddof=1) * smoothing_param ** 2
+        kde0 = np.sum(np.exp(-0.5 * d * d / cov)) / (len(d) * np.sqrt(2 * np.pi * cov))
+        out.append(max_bf if kde0 == 0 else min(1.0 / kde0, max_bf))
+    return out
+
+
+def format_bf_line(event_name, samples1, samples2, bf, header1, header2):
+    """One line of a ``.miso_bf`` file (``hypothesis_test.py:255-338``); header1/2 are the
+    parsed .miso headers of the two samples."""
+    from decimal import Decimal
+    s1, s2 = np.asarray(samples1, float), np.asarray(samples2, float)
+    c1, c2 = format_credible_intervals(event_name, s1), format_credible_intervals(event_name, s2)
+    m1, m2 = s1.mean(axis=0), s2.mean(axis=0)
+    if s1.shape[1] == 2:
+        q1 = Decimal(str(m1[0])).quantize(Decimal("0.01"))
+        q2 = Decimal(str(m2[0])).quantize(Decimal("0.01"))
+        mean1, mean2, diff, bfs = str(q1), str(q2), "%.2f" % (q1 - q2), "%.2f" % bf[0]
+    else:
+        mean1, mean2 = c1[1], c2[1]
+        diff = ",".join("%.2f" % v for v in (m1 - m2))
+        bfs = ",".join("%.2f" % max(v, 0) for v in bf)
+    return "\t".join([event_name, mean1, c1[2], c1[3], mean2, c2[2], c2[3], diff, bfs,
+                      header1.get("isoforms", ""), header1.get("counts", ""),
+                      header1.get("assigned_counts", ""), header2.get("counts", ""),
+                      header2.get("assigned_counts", ""), header1.get("chrom", "NA"),
+                      header1.get("strand", "NA"), header1.get("mRNA_starts", ""),
+                      header1.get("mRNA_ends", "")]) + "\n"

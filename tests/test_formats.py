@@ -53,3 +53,28 @@ def test_credible_interval_indices_follow_numpy_round():
 def test_count_isoform_assignments():
     assert mf.count_isoform_assignments(np.array([0, 2, 2, -1])) == [(0, 1), (1, 0), (2, 2)]
     assert mf.count_isoform_assignments(np.array([-1, -1])) == []   # range(max+1) is empty, reads_utils.py:42-45
+
+
+def test_bayes_factor_matches_scipy_kde():
+    """misopy's gaussian_kde_covfact(delta, 0.3) evaluated at 0 (hypothesis_test.py:41-57,168-169)."""
+    from scipy import stats
+
+    class kde_covfact(stats.gaussian_kde):
+        def covariance_factor(self):
+            return 0.3
+
+    rng = np.random.default_rng(3)
+    s1 = rng.dirichlet([4, 2, 6], size=450)
+    s2 = rng.dirichlet([5, 2, 5], size=450)
+    got = mf.bayes_factor(s1, s2)
+    for k in range(3):
+        want = 1.0 / kde_covfact(s1[:, k] - s2[:, k]).evaluate([0])[0]
+        assert abs(got[k] - want) <= 1e-9 * want
+    # peaked on the null
+    assert mf.bayes_factor(s1, s1 + 1e-4)[0] == 0.0
+    # far apart: capped
+    a = np.stack([np.full(100, 0.9) + rng.normal(0, 1e-3, 100), np.full(100, 0.1)], axis=1)
+    b = np.stack([np.full(100, 0.1) + rng.normal(0, 1e-3, 100), np.full(100, 0.9)], axis=1)
+    assert mf.bayes_factor(a, b)[0] == 1e12
+    line = mf.format_bf_line("ev", s1[:, :2], s2[:, :2], got, {"isoforms": "['a','b']"}, {})
+    assert line.count("\t") == len(mf.BF_HEADER) - 1

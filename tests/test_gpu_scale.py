@@ -66,3 +66,28 @@ def test_cfg2_and_cfg3_sized_batches_have_sane_posteriors(mb):
             if g < 300:
                 err.append(np.abs(s.mean(axis=1) - w.truth(g, K)).max())
         assert np.median(err) < 0.05, np.median(err)
+
+
+def test_two_sample_bayes_factor_on_device(mb):
+    """BASELINE config 5 in small: two samples of the same events (different reads), Delta psi
+    and Bayes factor per event on the device vs the numpy/scipy statement of
+    hypothesis_test.py."""
+    from miso_b200 import miso_format
+    wa = mb.Workload(1, 60, 600, 36, 250.0, 900.0, 4.0, seed=41)
+    wb = mb.Workload(1, 60, 600, 36, 250.0, 900.0, 4.0, seed=41)      # same genes/psi ...
+    wc = mb.Workload(1, 60, 600, 36, 250.0, 900.0, 4.0, seed=42)      # ... vs different psi
+    params = mb.make_params(1200, 200, 5, 2, seed=8)
+    pa, pb, pc = (mb.Plan().append(w) for w in (wa, wb, wc))
+    oa, ob, oc = pa.run(params), pb.run(mb.make_params(1200, 200, 5, 2, seed=9)), pc.run(params)
+    # genes of seed 41 and 42 differ in K: compare only a vs b (same structure)
+    cmp_ab = pa.compare(pb)
+    for g in range(60):
+        ra, rb = pa.gene_result(oa, g), pb.gene_result(ob, g)
+        want = miso_format.bayes_factor(ra["samples"].T, rb["samples"].T)
+        K = ra["samples"].shape[0]
+        np.testing.assert_allclose(cmp_ab[g, :K], want, rtol=1e-9)
+        np.testing.assert_allclose(cmp_ab[g, 8:8 + K], ra["samples"].mean(axis=1) - rb["samples"].mean(axis=1),
+                                   atol=1e-12)
+    assert (pa.info()[:, 0] != pc.info()[:, 0]).any()
+    with pytest.raises(mb.InternalError, match="different number of isoforms"):
+        pa.compare(pc)
