@@ -54,6 +54,18 @@ def algorithmic_bytes(info, S):
     return int((4 * R * (K + 2) + 8 * S * (K + 1) + 16 * K + 64).sum())
 
 
+def measured_traffic(workload, n_genes):
+    """dram__bytes_read + dram__bytes_write of one step from the committed ncu capture
+    (profiles/traffic.json), only when it was taken at this workload size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+        if t and t["events"] == n_genes:
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -344,7 +356,7 @@ def main():
                     "last_step_ms": {"h2d": timing[0], "kernels": timing[1], "d2h": timing[2]}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": how,
+                         "frac": achieved / peak, "traffic": measured_traffic(args.workload, G), "peak_source": how,
                          "algorithmic_bytes_per_step": alg,
                          "kernel": "chain_kernel<K,4>, K=2..8 (7 concurrent launches per step)",
                          "bucket_ms_per_step": {str(k): bucket[k] / args.steps for k in range(2, 9) if bucket[k] > 0}},
