@@ -148,6 +148,20 @@ def _cpu_worker(args):
     return n, time.perf_counter() - t0
 
 
+def usable_cores():
+    """Host cores this container may actually use: the scheduler affinity capped by the
+    cgroup CPU quota (the GPU boxes show 128 logical CPUs but cpu.max = 16 cores' worth;
+    more workers than that only thrash -- tools/cpu_probe.py)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_arm(wl, genes_per_core, cores=None):
     """Reference C path on `cores` processes over the first genes of the workload."""
     import concurrent.futures as cf
@@ -158,7 +172,7 @@ def cpu_arm(wl, genes_per_core, cores=None):
     kind_ref = "reference" if refdriver.available() else "port"
     if kind_ref == "port" and not refdriver.port_available():
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
-    cores = cores or os.cpu_count() or 1
+    cores = cores or usable_cores()
     n = cores * genes_per_core
     w = mb.Workload(wl["kind"], n, wl["reads"], READ_LEN, PE[0], PE[1], PE[2], seed=SEED, first_gene_id=0)
     slices = [[] for _ in range(cores)]
@@ -175,9 +189,10 @@ def cpu_arm(wl, genes_per_core, cores=None):
     busy = max(r[1] for r in res)
     iters = sum(r[0] for r in res)
     return dict(value=iters / busy, unit=UNIT, cores=cores, kind=kind_ref,
-                sample="%d genes of the workload (%d per core), %d iterations each, all %d host cores in "
-                       "parallel, %s; busy %.1fs wall %.1fs" % (
-                           n, genes_per_core, ITERS, cores,
+                sample="%d genes of the workload (%d per core), %d iterations each, %d worker processes = all "
+                       "usable host cores (%d logical CPUs visible, cgroup quota applied) in parallel, %s; busy "
+                       "%.1fs wall %.1fs" % (
+                           n, genes_per_core, ITERS, cores, os.cpu_count() or 0,
                            "reference's own MT19937 stream" if kind_ref == "reference" else "Philox stream",
                            busy, wall),
                 seconds=busy)

@@ -113,6 +113,11 @@ template <> struct TileMem<true> {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
   }
+  static __device__ __forceinline__ uint4 ld4(addr_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+  }
 };
 template <> struct TileMem<false> {
   using addr_t = const unsigned char *;
@@ -120,6 +125,11 @@ template <> struct TileMem<false> {
   static __device__ __forceinline__ uint32_t ld(addr_t a) {
     uint32_t v;
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(a));
+    return v;
+  }
+  static __device__ __forceinline__ uint4 ld4(addr_t a) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a));
     return v;
   }
 };
@@ -156,8 +166,8 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 // otherwise runs reassign_literal below instead.
 //   MODE 0: counts only.  MODE 1: + read score of the chosen isoform
 //   (miso_paired.c:157-163), needed when the next iteration records.
-template <int K, int MODE, bool SMEM>
-__device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes,
+template <int K, int MODE, bool SMEM, bool WIDE>
+__device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes, int flag_off,
                                               uint32_t ptab_s, const double (&psi)[K],
                                               unsigned long long n_u, int R2, uint32_t gene,
                                               uint32_t chain, const PhiloxKey &key, int paired,
@@ -172,19 +182,33 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
 #pragma unroll
   for (int k = 0; k < K; k++) G[k] = 0;
   double rp_lane = 0.0;
-  typename TM::addr_t a = rows + 4 * lane;
+  typename TM::addr_t a = rows + (WIDE ? 16 : 4) * lane;      // this lane's 4 codes of row 0 (before the phase shift)
+  typename TM::addr_t fa = rows + flag_off + 4 * lane;
+  // 16-bit codes: the lane's 4 codes start (3 - o) halfwords into its 8-halfword window
+  const int hs = 3 - o;
+  const bool hb = (hs >> 1) != 0;
+  const uint32_t hsh = 16u * (uint32_t) (hs & 1);
 
   for (int s = 0; s < nsteps; s++) {
     const int T = lane + 32 * s;
     uint32_t x[4];
     philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
-    uint32_t cw[K + 1];
+    uint32_t cw[K + 1], cx[WIDE ? K : 1];
 #pragma unroll
-    for (int k = 0; k <= K; k++) {
-      const uint32_t w0 = TM::ld(a + k * row_bytes), w1 = TM::ld(a + k * row_bytes + 4);
-      cw[k] = __byte_perm(w0, w1, sel);
+    for (int k = 0; k < K; k++) {
+      if (!WIDE) {
+        const uint32_t w0 = TM::ld(a + k * row_bytes), w1 = TM::ld(a + k * row_bytes + 4);
+        cw[k] = __byte_perm(w0, w1, sel);
+      } else {
+        const uint4 w = TM::ld4(a + k * row_bytes);
+        const uint32_t wa = hb ? w.y : w.x, wb = hb ? w.z : w.y, wc = hb ? w.w : w.z;
+        cw[k] = __funnelshift_r(wa, wb, hsh);      // codes of reads 0,1
+        cx[k] = __funnelshift_r(wb, wc, hsh);      // codes of reads 2,3
+      }
     }
-    a += 128;
+    cw[K] = __byte_perm(TM::ld(fa), TM::ld(fa + 4), sel);
+    a += WIDE ? 512 : 128;
+    fa += 128;
 #pragma unroll (kReadUnroll)
     for (int i = 0; i < 4; i++) {
       // flag byte: 1 = exactly two compatible isoforms (compare with nextup(rnd)), else 0
@@ -193,7 +217,8 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
       uint32_t code[K];
 #pragma unroll
       for (int k = 0; k < K; k++) {
-        code[k] = __byte_perm(cw[k], 0u, 0x4440u | (uint32_t) i);
+        if (!WIDE) code[k] = __byte_perm(cw[k], 0u, 0x4440u | (uint32_t) i);
+        else code[k] = __byte_perm(i < 2 ? cw[k] : cx[k], 0u, (i & 1) ? 0x4432u : 0x4410u);
         S = S + psi[k] * lds_f64(ptab_s + code[k] * 8u);     // CUMSUM, miso_paired.c:11-22
         C[k] = S;
       }
@@ -238,8 +263,8 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
 // per-read assignment, miso.c:943-946) and for passes the fast rule declined.
 // Not inlined and not unrolled over reads: it runs once or twice per chain.
 // psi_k is lane k's psi; returns lane k's count in cnt_k and the read score.
-template <int K, bool SMEM>
-__device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t rows, int row_bytes,
+template <int K, bool SMEM, bool WIDE>
+__device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t rows, int row_bytes, int flag_off,
                                               uint32_t ptab_s, double psi_k, unsigned long long n_u,
                                               int R2, uint32_t gene, uint32_t chain, const PhiloxKey &key,
                                               int paired, const int *__restrict__ L, int *cnt_k,
@@ -264,12 +289,13 @@ __device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t row
     for (int i = 0; i < 4; i++) {
       const int rank = 4 * T - o + i;
       if (rank < 0 || rank >= R2) continue;
-      const int byte = kTilePadFront + rank;
+      const int el = kTilePadFront + rank;
       auto code_at = [&](int k) -> uint32_t {
+        const int byte = WIDE ? 2 * el : el;
         const uint32_t w = TM::ld(rows + k * row_bytes + (byte & ~3));
-        return (w >> (8 * (byte & 3))) & 0xffu;
+        return WIDE ? (w >> (8 * (byte & 2))) & 0xffffu : (w >> (8 * (byte & 3))) & 0xffu;
       };
-      const bool two = code_at(K) == 1u;
+      const bool two = ((TM::ld(rows + flag_off + (el & ~3)) >> (8 * (el & 3))) & 0xffu) == 1u;
       const uint32_t xi = i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3];
       double S = 0.0, C[K];
       uint32_t code[K];
@@ -381,7 +407,7 @@ __device__ __forceinline__ double count_dot(int cnt_k, double v_k) {
   return s;
 }
 
-template <int K, bool SMEM>
+template <int K, bool SMEM, bool WIDE>
 __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_index, int chain,
                           typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s) {
   constexpr int len = K - 1;
@@ -393,7 +419,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   const int nfix_k = d.n_fixed[kk];
   const double lg_sum = d.lg_sum, lg_each = d.lg_each;
   const double sigma = d.sigma, sd = d.sd, covar = d.covar_const;
-  const int R2 = d.R2, row_bytes = d.row_bytes, paired = d.paired;
+  const int R2 = d.R2, row_bytes = d.row_bytes, flag_off = d.flag_off, paired = d.paired;
   const uint32_t gid = d.gene_id;
   const PhiloxKey &key = P.key;
   const int *L = d.L;
@@ -445,10 +471,10 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     }
     if (ok) {
       if (rec_next && !last)
-        reassign_pass<K, 1, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+        reassign_pass<K, 1, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
                                   cnt, rp_drawn);
       else
-        reassign_pass<K, 0, SMEM>(rows, row_bytes, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+        reassign_pass<K, 0, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
                                   cnt, rp_drawn);
       int c = 0;
 #pragma unroll
@@ -457,7 +483,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     }
     if (!ok) {   // final pass of chain 0, or a read whose weights underflow: literal rule
       int c = 0;
-      reassign_literal<K, SMEM>(rows, row_bytes, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired,
+      reassign_literal<K, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired,
                                 L, &c, &rp_drawn, last ? ass_out : nullptr);
       cnt_k = c + nfix_k;
     }
@@ -537,7 +563,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   }
 }
 
-template <int K, int WARPS, bool SMEM>
+template <int K, int WARPS, bool SMEM, bool WIDE>
 __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -562,7 +588,7 @@ __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(con
     const int gi = P.items[item / P.n_chains];
     const int chain = (int) (item % P.n_chains);
     const GeneDesc &d = P.desc[gi];
-    const uint32_t tile_bytes = (uint32_t) d.row_bytes * (K + 1);
+    const uint32_t tile_bytes = (uint32_t) d.tile_bytes;
     if (SMEM) {
       __syncwarp();
       if (lane == 0) {
@@ -572,9 +598,9 @@ __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(con
       }
       mbar_wait(bar, phase);
       phase ^= 1u;
-      run_chain<K, true>(P, d, gi, chain, TileMem<true>::base(slot), smem_u32(s_ptab));
+      run_chain<K, true, WIDE>(P, d, gi, chain, TileMem<true>::base(slot), smem_u32(s_ptab));
     } else {
-      run_chain<K, false>(P, d, gi, chain, TileMem<false>::base(P.tiles + d.tile_off), smem_u32(s_ptab));
+      run_chain<K, false, WIDE>(P, d, gi, chain, TileMem<false>::base(P.tiles + d.tile_off), smem_u32(s_ptab));
     }
   }
 }

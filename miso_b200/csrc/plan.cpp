@@ -201,7 +201,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   // src/miso.c:690-694
   if (overhang < 1 || overhang >= in.read_len / 2) { h.status = MISOB200_EINVAL; return; }
   const int n_codes = (int) plan.ptab.size();
-  if (n_codes > 256) { h.status = MISOB200_UNIMPLEMENTED; return; }   // byte codes only
+  if (n_codes > kMaxCodes) { h.status = MISOB200_UNIMPLEMENTED; return; }   // insert model wider than ptab in shared memory
 
   IsoView gv{K, in.exon_off + iso0, in.exon_start, in.exon_end};
   int isolen[kMaxIso], nex[kMaxIso];
@@ -328,19 +328,32 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   const int R2 = (int) drawn.size();
   h.R2 = R2; d.R2 = R2;
   h.rank_read.assign(drawn.begin(), drawn.end());
-  // row: 3 pad bytes, R2 codes, zero fill to a whole number of 128-read warp
-  // steps plus 16 spare bytes (a lane reads words T and T+1 of its step).
-  const int row_bytes = round_up(R2 + kTilePadFront, 128) + 16;
+  // code row: 3 pad elements, R2 codes, zero fill to a whole number of 128-read warp
+  // steps plus 16 spare bytes (a lane reads a little past its 4 reads); elements are
+  // bytes, or 16-bit when the insert model has more than 255 fragment lengths.  The
+  // flag row (1 = exactly two compatible isoforms) is always bytes.
+  const int cb = plan.wide ? 2 : 1;
+  const int padded = round_up(R2 + kTilePadFront, 128);
+  const int row_bytes = padded * cb + 16;
+  const int flag_row = padded + 16;
   d.row_bytes = row_bytes;
-  out.tile.assign((size_t) row_bytes * (K + 1), 0);
+  d.flag_off = row_bytes * K;
+  d.tile_bytes = row_bytes * K + flag_row;
+  out.tile.assign((size_t) d.tile_bytes, 0);
   for (int i = 0; i < R2; i++) {
     const int32_t *col = codes.data() + (size_t) drawn[i] * K;
     int nv = 0;
     for (int k = 0; k < K; k++) {
-      out.tile[(size_t) k * row_bytes + kTilePadFront + i] = (uint8_t) col[k];
+      uint8_t *row = out.tile.data() + (size_t) k * row_bytes;
+      if (plan.wide) {
+        row[2 * (kTilePadFront + i)] = (uint8_t) (col[k] & 0xff);
+        row[2 * (kTilePadFront + i) + 1] = (uint8_t) (col[k] >> 8);
+      } else {
+        row[kTilePadFront + i] = (uint8_t) col[k];
+      }
       nv += col[k] != 0;
     }
-    out.tile[(size_t) K * row_bytes + kTilePadFront + i] = (nv == 2) ? 1 : 0;   // flag row, see chain_kernel.cuh
+    out.tile[(size_t) d.flag_off + kTilePadFront + i] = (nv == 2) ? 1 : 0;
   }
   if (plan.keep_match) { h.codes = std::move(codes); h.order = std::move(order); }
 }
@@ -380,6 +393,7 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads) {
     if (paired) {
       if (!(in.frag_var > 0)) { set_error("plan_append: frag_var must be positive"); return MISOB200_EINVAL; }
       fragment_table(plan);
+      plan.wide = plan.ptab.size() > 256;
     } else {
       plan.ptab = {0.0, 1.0}; plan.frag_start = 0; plan.frag_len_n = 1;
     }

@@ -18,6 +18,7 @@
 namespace misob200 {
 
 constexpr int kMaxIso = MISOB200_MAX_ISO;
+constexpr int kMaxCodes = 4096;    // ptab entries that fit the shared-memory table (32 KB)
 constexpr int kTilePadFront = 3;   // bytes in front of rank 0 (stream misalignment, see chain_kernel.cu)
 
 // Device-visible per-gene descriptor (one per gene, 16-byte aligned, POD).
@@ -26,7 +27,7 @@ struct GeneDesc {
   long long sample_off;          // element offset into samples (f64)
   long long loglik_off;          // element offset into loglik (f64)
   long long drawn_off;           // element offset into the drawn-assignment arena (u8)
-  int K, R2, row_bytes, paired;
+  int K, R2, row_bytes, paired;   // row_bytes: one code row (u8 codes, or u16 when the plan is "wide")
   int n_fixed[kMaxIso];          // reads with exactly one compatible isoform
   int L[kMaxIso];                // PE: lp(j) = L[k] - j  (miso_paired.c:409-410)
   double offset[kMaxIso];        // SE log(effisolen_k) (miso.c:136) / PE assscores_k (miso_paired.c:418)
@@ -38,7 +39,9 @@ struct GeneDesc {
   unsigned gene_id;
   int rp_always;                 // some read score is not finite: keep readProb in every MH ratio
   int status;
-  int pad_;
+  int flag_off;                  // byte offset of the flag row (always u8) inside the tile
+  int tile_bytes;                // K code rows + flag row, multiple of 16
+  int pad_[2];
 };
 
 struct GeneHost {
@@ -58,6 +61,7 @@ struct Plan {
   double frag_mean = 0, frag_var = 0, num_devs = 0;
   int frag_start = 0, frag_len_n = 0;
   std::vector<double> ptab;              // ptab[0] = 0, ptab[j+1] = fragment prob j (SE: {0,1})
+  bool wide = false;                     // more than 255 fragment lengths: 16-bit codes
   std::vector<GeneDesc> desc;
   std::vector<GeneHost> host;
   std::vector<uint8_t> tiles;            // tile arena, each tile 16-byte aligned

@@ -247,14 +247,14 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   const auto &v = st->items[K];
   if (v.empty()) return 0;
   constexpr int WARPS = 4;
-  int max_row = 0;
-  for (int g : v) max_row = std::max(max_row, plan.desc[g].row_bytes);
+  int slot = 0;
+  for (int g : v) slot = std::max(slot, plan.desc[g].tile_bytes);
   const int ptab_bytes = ((int) plan.ptab.size() * 8 + 15) & ~15;
-  int slot = max_row * (K + 1);
   size_t smem = (size_t) ptab_bytes + WARPS * (16 + (size_t) slot);
   const size_t smem_cap = 227 * 1024;
   if (smem > smem_cap) { slot = 0; smem = (size_t) ptab_bytes + WARPS * 16; }   // stream tiles through L2
-  auto kern = slot ? chain_kernel<K, WARPS, true> : chain_kernel<K, WARPS, false>;
+  auto kern = plan.wide ? (slot ? chain_kernel<K, WARPS, true, true> : chain_kernel<K, WARPS, false, true>)
+                        : (slot ? chain_kernel<K, WARPS, true, false> : chain_kernel<K, WARPS, false, false>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));

@@ -181,7 +181,8 @@ int workload_create(int kind, int n_genes, int reads_per_gene, int read_len, dou
             if (v <= c) break;
           }
           if (j >= fp.size()) j = fp.size() - 1;
-          const int fl = fs + (int) j;
+          int fl = fs + (int) j;
+          if (fl > isolen[k]) fl = isolen[k];                  // rounding fell off the end of the table
           const int at = 1 + rng.below(isolen[k] - fl + 1);
           place_read(ies[k], iee[k], at, read_len, gb);
           place_read(ies[k], iee[k], at + fl - read_len, read_len, gb);

@@ -49,3 +49,17 @@ def test_summary_matches_numpy(mb):
         cnt = np.bincount(r["assignment"][r["assignment"] >= 0], minlength=s["n_iso"])
         np.testing.assert_array_equal(s["assigned_counts"], cnt)
         assert s["accepted"] == r["rundata"][5] and s["rejected"] == r["rundata"][6]
+
+
+def test_wide_insert_model_uses_16_bit_codes(mb, port):
+    """sd = 50 -> 401 fragment lengths: codes no longer fit a byte; the 16-bit tile variant
+    of the kernel must make the same decisions."""
+    w = mb.Workload(1, 20, 500, 36, 300.0, 2500.0, 4.0, seed=13)
+    plan = mb.Plan().append(w)
+    fp, fs = plan.fragment_table()
+    assert len(fp) > 255
+    params = mb.make_params(500, 100, 5, 2, seed=21)
+    out = plan.run(params)
+    for g in range(20):
+        want = oracle_gene(port, w.gene(g), True, params, gene_id=g, pe=(300.0, 2500.0, 4.0))
+        assert_gene_parity(plan.gene_result(out, g), want, tag="wide gene %d" % g)

@@ -104,3 +104,27 @@ def test_tile_layout_and_sizes():
     p = mb.make_params(1000, 100, 9, 3)
     ns, nl, na = plan.output_sizes(p)
     assert nl == 6 * 3 * 100 and na == n_reads and ns == int((info[:, 0] * 300).sum())
+
+
+def test_wide_insert_model_plan(port):
+    w = mb.Workload(1, 6, 300, 36, 300.0, 2500.0, 4.0, seed=13)
+    plan = mb.Plan(keep_match=True).append(w)
+    fp, fs = plan.fragment_table()
+    wfp, wfs = port.fragment_table(300.0, 2500.0, 4.0, 36)
+    np.testing.assert_array_equal(fp, wfp)
+    assert fs == wfs and len(fp) == 401
+    info = plan.info()
+    assert (info[:, 4] == 0).all()
+    for g in range(6):
+        ex, iso, pos, cig = w.gene(g)
+        codes, order = plan.match(g)
+        want = port.match_pe(ex, iso, pos, cig, 36, 300.0, 2500.0, 4.0)
+        np.testing.assert_array_equal(np.where(codes > 0, codes - 1 + fs, -1), want["fraglen"])
+        np.testing.assert_array_equal(order, want["order"])
+    _, _, tile_bytes = plan.size()
+    want_bytes = sum(((int(r2) + 3 + 127) // 128 * 128 * 2 + 16) * int(k) + (int(r2) + 3 + 127) // 128 * 128 + 16
+                     for k, _, r2, _, _ in info)
+    assert tile_bytes == want_bytes
+    # an insert model too wide even for 16-bit tiles in shared memory is refused, not mis-run
+    big = mb.Plan().append(mb.Workload(1, 1, 10, 36, 3000.0, 360000.0, 4.0, seed=1))
+    assert big.info()[0, 4] == 12
