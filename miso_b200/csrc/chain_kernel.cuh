@@ -113,9 +113,11 @@ template <> struct TileMem<true> {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
   }
+  // 16 bytes from an 8-byte aligned address (two 8-byte loads)
   static __device__ __forceinline__ uint4 ld4(addr_t a) {
     uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+8];" : "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
   }
 };
@@ -129,7 +131,8 @@ template <> struct TileMem<false> {
   }
   static __device__ __forceinline__ uint4 ld4(addr_t a) {
     uint4 v;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a));
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a));
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2+8];" : "=r"(v.z), "=r"(v.w) : "l"(a));
     return v;
   }
 };
@@ -182,7 +185,8 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
 #pragma unroll
   for (int k = 0; k < K; k++) G[k] = 0;
   double rp_lane = 0.0;
-  typename TM::addr_t a = rows + (WIDE ? 16 : 4) * lane;      // this lane's 4 codes of row 0 (before the phase shift)
+  // this lane's window of row 0: elements 4*lane .. 4*lane+7 (4 codes after the phase shift)
+  typename TM::addr_t a = rows + (WIDE ? 8 : 4) * lane;
   typename TM::addr_t fa = rows + flag_off + 4 * lane;
   // 16-bit codes: the lane's 4 codes start (3 - o) halfwords into its 8-halfword window
   const int hs = 3 - o;
@@ -207,7 +211,7 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
       }
     }
     cw[K] = __byte_perm(TM::ld(fa), TM::ld(fa + 4), sel);
-    a += WIDE ? 512 : 128;
+    a += WIDE ? 256 : 128;
     fa += 128;
 #pragma unroll (kReadUnroll)
     for (int i = 0; i < 4; i++) {
