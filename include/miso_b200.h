@@ -129,6 +129,16 @@ int misob200_plan_append(misob200_plan_t *plan, const misob200_reads_t *reads,
    misob200_plan_gene_match (parity tests; costs 4 bytes per read x isoform) */
 int misob200_plan_keep_match(misob200_plan_t *plan, int on);
 
+/* tile format of later appends: -1 (default) class tiles whenever a gene has at
+   most 254 weight classes among its drawing reads, dense tiles otherwise;
+   0 dense tiles only (the general fp64 pass; parity tests run both) */
+int misob200_plan_tile_format(misob200_plan_t *plan, int format);
+/* per gene: tile format chosen (0 dense, 1 class), number of weight classes
+   (class format), tile bytes */
+int misob200_plan_gene_tile(const misob200_plan_t *plan, int32_t gene,
+			    int32_t *format, int32_t *n_weight_classes,
+			    int32_t *tile_bytes);
+
 int misob200_plan_size(const misob200_plan_t *plan, int32_t *n_genes,
 		       int64_t *n_reads, int64_t *tile_bytes);
 /* per gene: K, number of reads/pairs R, reads that draw each pass R2,

@@ -162,11 +162,14 @@ class Workload:
 
 
 class Plan:
-    def __init__(self, keep_match=False):
+    def __init__(self, keep_match=False, tile_format=-1):
+        """tile_format: -1 class tiles where a gene allows it (default), 0 dense tiles only."""
         self.h = C.c_void_p()
         check(lib.misob200_plan_create(C.byref(self.h)))
         if keep_match:
             check(lib.misob200_plan_keep_match(self.h, 1))
+        if tile_format != -1:
+            check(lib.misob200_plan_tile_format(self.h, tile_format))
         self._info = None
 
     def append(self, reads, n_threads=0):
@@ -188,6 +191,16 @@ class Plan:
         g, r, t = C.c_int32(), C.c_int64(), C.c_int64()
         check(lib.misob200_plan_size(self.h, C.addressof(g), C.addressof(r), C.addressof(t)))
         return g.value, r.value, t.value
+
+    def tile_info(self):
+        """int32 array [n_genes, 3]: tile format (0 dense, 1 class), weight classes, tile bytes."""
+        G = self.size()[0]
+        out = np.zeros((G, 3), np.int32)
+        v = [C.c_int32() for _ in range(3)]
+        for g in range(G):
+            check(lib.misob200_plan_gene_tile(self.h, g, *[C.addressof(x) for x in v]))
+            out[g] = [x.value for x in v]
+        return out
 
     def info(self):
         """int32 array [n_genes, 5]: K, R, R2, n_classes, status."""

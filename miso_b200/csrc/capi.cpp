@@ -52,6 +52,20 @@ int misob200_plan_keep_match(misob200_plan_t *plan, int on) {
   plan->p.keep_match = on != 0;
   return 0;
 }
+int misob200_plan_tile_format(misob200_plan_t *plan, int format) {
+  if (!plan || format < -1 || format > 1) return MISOB200_EINVAL;
+  plan->p.force_format = format;
+  return 0;
+}
+int misob200_plan_gene_tile(const misob200_plan_t *plan, int32_t gene, int32_t *format, int32_t *n_weight_classes,
+                            int32_t *tile_bytes) {
+  if (!plan || gene < 0 || (size_t) gene >= plan->p.desc.size()) return MISOB200_EINVAL;
+  const GeneDesc &d = plan->p.desc[gene];
+  if (format) *format = d.format;
+  if (n_weight_classes) *n_weight_classes = d.ncls;
+  if (tile_bytes) *tile_bytes = d.tile_bytes;
+  return 0;
+}
 int misob200_plan_append(misob200_plan_t *plan, const misob200_reads_t *reads, int n_threads) {
   if (!plan || !reads) { set_error("plan_append: null argument"); return MISOB200_EINVAL; }
   if (plan->p.dev) release_device(plan->p);

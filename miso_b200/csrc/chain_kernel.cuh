@@ -31,14 +31,9 @@
 
 #include "philox.cuh"
 #include "plan.hpp"
-
-#ifndef MISOB200_READ_UNROLL
-#define MISOB200_READ_UNROLL 2   /* measured: 2 beats 4 (I-cache) and 1 (ILP), profiles/README.md */
-#endif
+#include "tile_mem.cuh"
 
 namespace misob200 {
-
-constexpr int kReadUnroll = MISOB200_READ_UNROLL;   // reads of a lane's step unrolled together
 
 struct ChainParams {
   const GeneDesc *desc;
@@ -57,287 +52,18 @@ struct ChainParams {
   int n_iters, burn_in, lag, start;
   PhiloxKey key;
   int slot_bytes;            // shared-memory bytes per warp for a tile (0: stream tiles from L2)
+  // class format only
+  const double *neglog;      // neglog[n] = -log(n), n < n_neglog (read scores, miso_paired.c:409-411)
+  int n_neglog;
+  int thr_bytes;             // shared-memory bytes per warp for the threshold rows (after the slot)
 };
 
-__device__ __forceinline__ double shfl_d(double v, int src) {
-  return __shfl_sync(0xffffffffu, v, src);
-}
+}  // namespace misob200
 
-// ---- TMA bulk copy global -> shared, completion on an mbarrier ---------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t) __cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
+#include "dense_pass.cuh"
+#include "class_pass.cuh"
 
-// ---- explicit address-space loads ------------------------------------------------
-// The tile normally sits in shared memory (32-bit shared addresses, LDS); genes
-// whose tile does not fit in a slot are streamed from global/L2 instead.
-template <bool SMEM> struct TileMem;
-template <> struct TileMem<true> {
-  using addr_t = uint32_t;
-  static __device__ __forceinline__ addr_t base(const void *p) { return smem_u32(p); }
-  static __device__ __forceinline__ uint32_t ld(addr_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-  }
-  // 16 bytes from an 8-byte aligned address (two 8-byte loads)
-  static __device__ __forceinline__ uint4 ld4(addr_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
-    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+8];" : "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-  }
-};
-template <> struct TileMem<false> {
-  using addr_t = const unsigned char *;
-  static __device__ __forceinline__ addr_t base(const void *p) { return static_cast<addr_t>(p); }
-  static __device__ __forceinline__ uint32_t ld(addr_t a) {
-    uint32_t v;
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(a));
-    return v;
-  }
-  static __device__ __forceinline__ uint4 ld4(addr_t a) {
-    uint4 v;
-    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(a));
-    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2+8];" : "=r"(v.z), "=r"(v.w) : "l"(a));
-    return v;
-  }
-};
-__device__ __forceinline__ double lds_f64(uint32_t a) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-  return v;
-}
-
-// ---- one reassignment pass ----------------------------------------------------
-// src/miso.c:30-91 / src/miso_paired.c:24-86 for the R2 reads that draw.
-// Lane handles Philox block Q0+T (uniform indices 4(Q0+T)..+3) for
-// T = lane + 32*step, i.e. ranks 4T-o .. 4T-o+3 with o = n_u & 3: the stream is
-// sequential (the accept draw is conditional, miso.c:870), so a pass starts at
-// an arbitrary phase o.  Rows carry 3 zero bytes in front and zero padding
-// behind; a zero code means "incompatible" (weight psi_k * ptab[0] = 0).
-//
-// Choice rule.  With C_k the running sum of psi_k * p_k over ALL isoforms
-// (incompatible ones add an exact 0.0, so C_k is the reference's cumsum at the
-// last compatible isoform <= k) and rnd = u * C_{K-1}:
-//   >= 3 compatible: first w with !(rnd > cumsum[w])      (miso.c:78)
-//      2 compatible: rnd <  cumsum[0] ? first : second    (miso.c:71)
-// Both are "the number of k < K-1 whose test says go on": rnd > C_k, resp.
-// rnd >= C_k, and rnd >= C  <=>  nextup(rnd) > C for rnd >= 0 -- one integer add
-// on the bit pattern per read.  (Leading incompatible isoforms have C_k = 0 <
-// rnd and are skipped, the others repeat their predecessor's verdict.)  So the
-// pass only keeps G_k = #{reads with test_k true}; the per-isoform counts the MH
-// ratio needs are n_0 = R2 - G_0, n_k = G_{k-1} - G_k, n_{K-1} = G_{K-2}.
-// Phantom ranks (padding) have rnd = 0 and C_k = 0: no test is true.
-// The argument needs 0 < rnd < C_{K-1}, true whenever C_{K-1} is a normal number
-// (u is in [2^-33, 1 - 2^-33]).  Every drawing read has a compatible isoform, so
-// C_{K-1} >= min_k psi_k * min nonzero ptab: the caller checks that bound once per
-// pass (>= 1e-290, which also rules out a negative psi_{K-1} = 1 - sum) and
-// otherwise runs reassign_literal below instead.
-//   MODE 0: counts only.  MODE 1: + read score of the chosen isoform
-//   (miso_paired.c:157-163), needed when the next iteration records.
-template <int K, int MODE, bool SMEM, bool WIDE>
-__device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes, int flag_off,
-                                              uint32_t ptab_s, const double (&psi)[K],
-                                              unsigned long long n_u, int R2, uint32_t gene,
-                                              uint32_t chain, const PhiloxKey &key, int paired,
-                                              const int *__restrict__ L, int (&cnt)[K], double &rp) {
-  using TM = TileMem<SMEM>;
-  const int lane = threadIdx.x & 31;
-  const int o = (int) (n_u & 3ull);
-  const uint32_t Q0 = (uint32_t) (n_u >> 2);
-  const int nsteps = (R2 + o + 127) >> 7;
-  const uint32_t sel = 0x3210u + 0x1111u * (uint32_t) (3 - o);
-  int G[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) G[k] = 0;
-  double rp_lane = 0.0;
-  // this lane's window of row 0: elements 4*lane .. 4*lane+7 (4 codes after the phase shift)
-  typename TM::addr_t a = rows + (WIDE ? 8 : 4) * lane;
-  typename TM::addr_t fa = rows + flag_off + 4 * lane;
-  // 16-bit codes: the lane's 4 codes start (3 - o) halfwords into its 8-halfword window
-  const int hs = 3 - o;
-  const bool hb = (hs >> 1) != 0;
-  const uint32_t hsh = 16u * (uint32_t) (hs & 1);
-
-  for (int s = 0; s < nsteps; s++) {
-    const int T = lane + 32 * s;
-    uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
-    uint32_t cw[K + 1], cx[WIDE ? K : 1];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      if (!WIDE) {
-        const uint32_t w0 = TM::ld(a + k * row_bytes), w1 = TM::ld(a + k * row_bytes + 4);
-        cw[k] = __byte_perm(w0, w1, sel);
-      } else {
-        const uint4 w = TM::ld4(a + k * row_bytes);
-        const uint32_t wa = hb ? w.y : w.x, wb = hb ? w.z : w.y, wc = hb ? w.w : w.z;
-        cw[k] = __funnelshift_r(wa, wb, hsh);      // codes of reads 0,1
-        cx[k] = __funnelshift_r(wb, wc, hsh);      // codes of reads 2,3
-      }
-    }
-    cw[K] = __byte_perm(TM::ld(fa), TM::ld(fa + 4), sel);
-    a += WIDE ? 256 : 128;
-    fa += 128;
-#pragma unroll (kReadUnroll)
-    for (int i = 0; i < 4; i++) {
-      // flag byte: 1 = exactly two compatible isoforms (compare with nextup(rnd)), else 0
-      const uint32_t two = __byte_perm(cw[K], 0u, 0x4440u | (uint32_t) i);
-      double S = 0.0, C[K];
-      uint32_t code[K];
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        if (!WIDE) code[k] = __byte_perm(cw[k], 0u, 0x4440u | (uint32_t) i);
-        else code[k] = __byte_perm(i < 2 ? cw[k] : cx[k], 0u, (i & 1) ? 0x4432u : 0x4410u);
-        S = S + psi[k] * lds_f64(ptab_s + code[k] * 8u);     // CUMSUM, miso_paired.c:11-22
-        C[k] = S;
-      }
-      const double rnd = uniform_from_word(MISOB200_READ_UNROLL == 4 ? x[i] : (i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3])) * S;          // miso.c:70,76
-      const double rc = __longlong_as_double(__double_as_longlong(rnd) + (long long) two);
-      int chosen = 0;
-#pragma unroll
-      for (int k = 0; k < K - 1; k++) {
-        const bool go_on = rc > C[k];
-        G[k] += go_on;
-        if (MODE == 1) chosen += go_on;
-      }
-      if (MODE == 1) {
-        const int rank = 4 * T - o + i;
-        if (rank >= 0 && rank < R2 && paired) {
-          uint32_t cc = code[0];
-#pragma unroll
-          for (int k = 1; k < K; k++)
-            if (chosen == k) cc = code[k];
-          const int Lc = __ldg(L + chosen);
-          const double lp = (double) (Lc - ((int) cc - 1));
-          rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < K - 1; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]);
-  cnt[0] = R2 - G[0];
-#pragma unroll
-  for (int k = 1; k < K - 1; k++) cnt[k] = G[k - 1] - G[k];
-  cnt[K - 1] = G[K - 2];
-  if (MODE == 1) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
-    rp = rp_lane;
-  }
-}
-
-// The literal rule of miso.c:59-83, read by read, with the compatibility tests
-// spelled out.  Used for the final pass of chain 0 (which has to emit the
-// per-read assignment, miso.c:943-946) and for passes the fast rule declined.
-// Not inlined and not unrolled over reads: it runs once or twice per chain.
-// psi_k is lane k's psi; returns lane k's count in cnt_k and the read score.
-template <int K, bool SMEM, bool WIDE>
-__device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t rows, int row_bytes, int flag_off,
-                                              uint32_t ptab_s, double psi_k, unsigned long long n_u,
-                                              int R2, uint32_t gene, uint32_t chain, const PhiloxKey &key,
-                                              int paired, const int *__restrict__ L, int *cnt_k,
-                                              double *rp, uint8_t *__restrict__ ass_out) {
-  using TM = TileMem<SMEM>;
-  const int lane = threadIdx.x & 31;
-  const int o = (int) (n_u & 3ull);
-  const uint32_t Q0 = (uint32_t) (n_u >> 2);
-  const int nsteps = (R2 + o + 127) >> 7;
-  double psi[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) psi[k] = shfl_d(psi_k, k);
-  int n[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) n[k] = 0;
-  double rp_lane = 0.0;
-  for (int s = 0; s < nsteps; s++) {
-    const int T = lane + 32 * s;
-    uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
-#pragma unroll 1
-    for (int i = 0; i < 4; i++) {
-      const int rank = 4 * T - o + i;
-      if (rank < 0 || rank >= R2) continue;
-      const int el = kTilePadFront + rank;
-      auto code_at = [&](int k) -> uint32_t {
-        const int byte = WIDE ? 2 * el : el;
-        const uint32_t w = TM::ld(rows + k * row_bytes + (byte & ~3));
-        return WIDE ? (w >> (8 * (byte & 2))) & 0xffffu : (w >> (8 * (byte & 3))) & 0xffu;
-      };
-      const bool two = ((TM::ld(rows + flag_off + (el & ~3)) >> (8 * (el & 3))) & 0xffu) == 1u;
-      const uint32_t xi = i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3];
-      double S = 0.0, C[K];
-      uint32_t code[K];
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        code[k] = code_at(k);
-        S = S + psi[k] * lds_f64(ptab_s + code[k] * 8u);
-        C[k] = S;
-      }
-      const double rnd = uniform_from_word(xi) * S;
-      int chosen = -1;
-      uint32_t cc = 0;
-#pragma unroll
-      for (int k = K - 1; k >= 0; k--) {
-        const bool valid = code[k] != 0u;
-        const bool hit = two ? (rnd < C[k]) : (rnd <= C[k]);     // miso.c:71 / :78
-        if (valid && (hit || chosen < 0)) { chosen = k; cc = code[k]; }
-      }
-#pragma unroll
-      for (int k = 0; k < K; k++) n[k] += (chosen == k);
-      if (chosen >= 0 && paired) {
-        const double lp = (double) (__ldg(L + chosen) - ((int) cc - 1));
-        rp_lane += -log(lp) + lds_f64(ptab_s + cc * 8u);
-      }
-      if (ass_out) ass_out[rank] = (uint8_t) chosen;
-    }
-  }
-  int mine = 0;
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    const int t = __reduce_add_sync(0xffffffffu, n[k]);
-    if (lane == k) mine = t;
-  }
-  *cnt_k = mine;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
-  *rp = rp_lane;
-}
+namespace misob200 {
 
 // Everything derived from a candidate alpha (lane i < K-1 holds alpha_i).
 struct Derived {
@@ -411,9 +137,9 @@ __device__ __forceinline__ double count_dot(int cnt_k, double v_k) {
   return s;
 }
 
-template <int K, bool SMEM, bool WIDE>
+template <int K, bool SMEM, bool WIDE, int FMT>
 __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_index, int chain,
-                          typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s) {
+                          typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s, const ClassRef &cr) {
   constexpr int len = K - 1;
   const int lane = threadIdx.x & 31;
   const int kk = lane < K ? lane : K - 1;
@@ -424,6 +150,11 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   const double lg_sum = d.lg_sum, lg_each = d.lg_each;
   const double sigma = d.sigma, sd = d.sd, covar = d.covar_const;
   const int R2 = d.R2, row_bytes = d.row_bytes, flag_off = d.flag_off, paired = d.paired;
+  const int ucode_off = d.ucode_off;
+  int g_always[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) g_always[k] = FMT == 1 ? d.g_always[k] : 0;
+  int thr_state = 0;       // class format: 0 thresholds stale (psi changed), 1 valid, 2 declined for this psi
   const uint32_t gid = d.gene_id;
   const PhiloxKey &key = P.key;
   const int *L = d.L;
@@ -473,22 +204,40 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
       }
       ok = !ok && (pmin * P.ptab_min >= 1e-290);        // fast rule valid for every read of this pass
     }
-    if (ok) {
-      if (rec_next && !last)
-        reassign_pass<K, 1, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
-                                  cnt, rp_drawn);
-      else
-        reassign_pass<K, 0, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
-                                  cnt, rp_drawn);
-      int c = 0;
+    if (FMT == 0) {
+      if (ok) {
+        if (rec_next && !last)
+          reassign_pass<K, 1, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+                                    cnt, rp_drawn);
+        else
+          reassign_pass<K, 0, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+                                    cnt, rp_drawn);
+        int c = 0;
 #pragma unroll
-      for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
-      cnt_k = c + nfix_k;
-    }
-    if (!ok) {   // final pass of chain 0, or a read whose weights underflow: literal rule
+        for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
+        cnt_k = c + nfix_k;
+      }
+      if (!ok) {   // final pass of chain 0, or a read whose weights underflow: literal rule
+        int c = 0;
+        reassign_literal<K, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired,
+                                  L, &c, &rp_drawn, last ? ass_out : nullptr);
+        cnt_k = c + nfix_k;
+      }
+    } else {
+      if (ok && thr_state == 0) thr_state = thr_update<K>(cr, ptab_s, psi_r) ? 2 : 1;
+      ok = ok && thr_state == 1;
       int c = 0;
-      reassign_literal<K, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired,
-                                L, &c, &rp_drawn, last ? ass_out : nullptr);
+      if (ok && !(rec_next && !last)) {
+        class_pass<K, SMEM>(rows, cr, n_u, R2, gid, (uint32_t) chain, key, g_always, cnt);
+#pragma unroll
+        for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
+      } else if (ok) {
+        class_pass_rp<K, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+                                     P.neglog, P.n_neglog, &c, &rp_drawn);
+      } else {     // final pass of chain 0, thresholds declined, or weights that underflow
+        class_literal<K, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+                                     P.neglog, P.n_neglog, &c, &rp_drawn, last ? ass_out : nullptr);
+      }
       cnt_k = c + nfix_k;
     }
     n_u += (unsigned long long) R2;
@@ -504,7 +253,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     const double alphaN = alpha + sd * next_normals((uint32_t) (m + 1) * (uint32_t) len);
     const Derived nw = derive<K>(alphaN, offset_k, hyper_m1_k, lg_sum, lg_each);
     if (m < 0) {
-      alpha = alphaN; cur = nw;
+      alpha = alphaN; cur = nw; thr_state = 0;
     } else {
     // ---- joint scores (miso.c:524-529) -----------------------------------
     double rp;
@@ -536,7 +285,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     }
     double cJS = pcJS;
     if (accept) {
-      alpha = alphaN; cur = nw; cJS = ppJS; acc++;
+      alpha = alphaN; cur = nw; cJS = ppJS; acc++; thr_state = 0;
     } else {
       rej++;
     }
@@ -567,14 +316,18 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   }
 }
 
-template <int K, int WARPS, bool SMEM, bool WIDE>
+// FMT 0: dense tiles (dense_pass.cuh); FMT 1: class tiles (class_pass.cuh).
+// Shared memory: [ptab | per warp {mbarrier (16 B), slot, threshold rows (FMT 1)}].  The slot
+// holds the gene's whole tile (SMEM), or only its class records when the rows are streamed
+// from global/L2 (FMT 1, !SMEM).
+template <int K, int WARPS, bool SMEM, bool WIDE, int FMT>
 __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // layout: [ptab | per-warp {mbarrier(16 B), tile slot}]
   double *s_ptab = reinterpret_cast<double *>(smem);
   const int ptab_bytes = (P.n_ptab * 8 + 15) & ~15;
-  unsigned char *wbase = smem + ptab_bytes + (size_t) warp * (16 + P.slot_bytes);
+  const int thr_bytes = FMT == 1 ? P.thr_bytes : 0;
+  unsigned char *wbase = smem + ptab_bytes + (size_t) warp * (16 + P.slot_bytes + thr_bytes);
   uint64_t *bar = reinterpret_cast<uint64_t *>(wbase);
   unsigned char *slot = wbase + 16;
 
@@ -593,19 +346,39 @@ __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(con
     const int chain = (int) (item % P.n_chains);
     const GeneDesc &d = P.desc[gi];
     const uint32_t tile_bytes = (uint32_t) d.tile_bytes;
+    ClassRef cr;
+    cr.ncls = FMT == 1 ? d.ncls : 0;
+    cr.thr_s = smem_u32(slot + P.slot_bytes);
+    cr.rec_s = smem_u32(slot) + (SMEM ? (uint32_t) d.cls_off : 0u);
+    cr.meta_s = cr.rec_s + 16u * (uint32_t) cr.ncls;
+    __syncwarp();
     if (SMEM) {
-      __syncwarp();
       if (lane == 0) {
         fence_proxy_async();
         mbar_expect_tx(bar, tile_bytes);
         tma_bulk_g2s(slot, P.tiles + d.tile_off, tile_bytes, bar);
       }
+    } else if (FMT == 1) {
+      // rows stay in global memory; the class records are small and go to the slot
+      const uint4 *src = reinterpret_cast<const uint4 *>(P.tiles + d.tile_off + d.cls_off);
+      const int n16 = (int) (tile_bytes - (uint32_t) d.cls_off) >> 4;
+      for (int i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(slot)[i] = __ldg(src + i);
+    }
+    if (FMT == 1 && lane == 0) {      // null class of the padding: no test is ever true
+      uint32_t never[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) never[k] = 0xffffffffu;
+      Thr<K>::store(cr.thr_s + (uint32_t) (Thr<K>::TS * cr.ncls), never);
+    }
+    if (SMEM) {
       mbar_wait(bar, phase);
       phase ^= 1u;
-      run_chain<K, true, WIDE>(P, d, gi, chain, TileMem<true>::base(slot), smem_u32(s_ptab));
-    } else {
-      run_chain<K, false, WIDE>(P, d, gi, chain, TileMem<false>::base(P.tiles + d.tile_off), smem_u32(s_ptab));
     }
+    __syncwarp();
+    if (SMEM)
+      run_chain<K, true, WIDE, FMT>(P, d, gi, chain, TileMem<true>::base(slot), smem_u32(s_ptab), cr);
+    else
+      run_chain<K, false, WIDE, FMT>(P, d, gi, chain, TileMem<false>::base(P.tiles + d.tile_off), smem_u32(s_ptab), cr);
   }
 }
 

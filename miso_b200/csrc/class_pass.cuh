@@ -1,0 +1,325 @@
+// miso_b200/csrc/class_pass.cuh -- reassignment passes over CLASS tiles (format 1).
+//
+// The reference decides read r of a pass (src/miso.c:59-83, src/miso_paired.c:45-78) by
+//     rnd = u_r * C_{K-1},   chosen = #{k < K-1 : rnd > C_k}   (>= for two compatible)
+// with C_k the running sum of psi_j * p_{r,j}.  u_r = (w_r + 0.5) * 2^-32 comes from
+// one 32-bit Philox word, rnd is monotone in w_r, so every test is an INTEGER
+// threshold on the raw word:  test k true  <=>  w_r > t_k.  t_k depends on the read
+// only through the direction of its weight vector -- its weight class
+// (plan.cpp) -- so it is computed once per (class, iteration) in fp64 by one lane,
+// and the per-read work of a pass shrinks to "load the class's K-1 thresholds,
+// compare, count": no fp64, no probability lookups, one byte of tile per read.
+//
+// Exactness.  Let rho_k = C_k / C_{K-1} in exact arithmetic.  The reference's test is
+// true iff w + 0.5 > 2^32 rho_k (1 + eta), where eta collects the roundings of its
+// products, sums and of u * C (|eta| <= (2n+3) 2^-53 for n <= 8 compatible isoforms).
+// thr_update computes tau = C_k * (2^32 / C_{K-1}) - 0.5 with its own roundings of the
+// same size; both errors together stay below 1.8e-5 in units of w (tau <= 2^32, so
+// absolute errors are ~2^32 * 17 * 2^-53 + two half-ulps of 2^32).  If tau lies more
+// than kThrMargin = 2^-15 away from every integer, no integer w can fall between the
+// reference's boundary and tau, hence  test  <=>  w > floor(tau)  for every read of
+// the class -- for the `>` and the `>=` rule alike.  Otherwise (probability
+// ~6e-5 per threshold) the pass is declined and the caller runs the literal fp64
+// rule for this iteration.  Uniform-code classes use weight 1.0 in place of
+// ptab[code]: the common factor cancels in rho_k and its rounding is inside eta.
+// tests/test_thresholds.py checks the claim against the oracle's arithmetic at the
+// boundary words.
+#pragma once
+#include "philox.cuh"
+#include "plan.hpp"
+#include "tile_mem.cuh"
+
+namespace misob200 {
+
+constexpr double kThrMargin = 0x1p-15;
+
+template <int K> struct Thr {
+  static constexpr int NT = K - 1;                                          // thresholds per class
+  static constexpr int TS = NT <= 1 ? 4 : NT <= 2 ? 8 : NT <= 4 ? 16 : 32;   // bytes per class row
+  static __device__ __forceinline__ void load(uint32_t a, uint32_t (&t)[8]) {
+    if (NT == 1) {
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t[0]) : "r"(a));
+    } else if (NT == 2) {
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(t[0]), "=r"(t[1]) : "r"(a));
+    } else {
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]) : "r"(a));
+      if (NT == 5) asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(t[4]) : "r"(a));
+      if (NT == 6) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+16];" : "=r"(t[4]), "=r"(t[5]) : "r"(a));
+      if (NT == 7)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]) : "r"(a));
+    }
+  }
+  static __device__ __forceinline__ void store(uint32_t a, const uint32_t (&t)[8]) {
+    if (NT == 1) {
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(t[0]) : "memory");
+    } else if (NT == 2) {
+      asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(t[0]), "r"(t[1]) : "memory");
+    } else {
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
+      if (NT > 4)
+        asm volatile("st.shared.v4.u32 [%0+16], {%1,%2,%3,%4};" ::"r"(a), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]) : "memory");
+    }
+  }
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+
+// Shared-memory addresses of a gene's class data (all per warp).
+struct ClassRef {
+  uint32_t rec_s;    // ncls x 8 u16 ptab indices (0 = incompatible)
+  uint32_t meta_s;   // ncls x u32: bits 0-7 first compatible isoform, bit 8 uniform-code class
+  uint32_t thr_s;    // (ncls + 1) x Thr<K>::TS bytes, row ncls = null class (no test ever true)
+  int ncls;
+};
+
+// ---- thresholds of every class for the current psi ---------------------------
+// Lane c handles class c (c += 32).  Returns true (warp-uniform) when some threshold is
+// too close to an integer to be trusted -- the caller then runs the literal rule.
+template <int K>
+__device__ __forceinline__ bool thr_update(const ClassRef &cr, uint32_t ptab_s, const double (&psi)[K]) {
+  constexpr int NT = Thr<K>::NT;
+  const int lane = threadIdx.x & 31;
+  bool bad = false;
+  for (int c = lane; c < cr.ncls; c += 32) {
+    uint4 rec;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w) : "r"(cr.rec_s + 16u * c));
+    const uint32_t rw[4] = {rec.x, rec.y, rec.z, rec.w};
+    const int first = (int) (lds_u32(cr.meta_s + 4u * c) & 0xffu);
+    double S = 0.0, C[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const uint32_t idx = (k & 1) ? (rw[k >> 1] >> 16) : (rw[k >> 1] & 0xffffu);
+      S = S + psi[k] * lds_f64(ptab_s + idx * 8u);      // CUMSUM, miso_paired.c:11-22
+      C[k] = S;
+    }
+    const double inv = 4294967296.0 / S;
+    uint32_t t[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) t[k] = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < NT; k++) {
+      const double tau = C[k] * inv - 0.5;
+      const uint32_t tk = __double2uint_rz(tau);         // saturating
+      const double fr = tau - (double) tk;
+      const bool good = fr > kThrMargin && fr < 1.0 - kThrMargin;
+      // isoforms before the first compatible one: C_k is an exact 0 < rnd, the test is
+      // always true; those reads are counted by GeneDesc.g_always, the row says "never"
+      if (k >= first) {
+        t[k] = tk;
+        bad = bad || !good;
+      }
+    }
+    Thr<K>::store(cr.thr_s + (uint32_t) (Thr<K>::TS * c), t);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  __syncwarp();
+  return bad;
+}
+
+// ---- one reassignment pass, counts only -----------------------------------------
+// Lane handles Philox block Q0+T (uniform indices 4(Q0+T)..+3), T = lane + 32*step,
+// i.e. ranks 4T-o .. 4T-o+3 with o = n_u & 3 (the stream is sequential and the accept
+// draw is conditional, miso.c:870, so a pass starts at an arbitrary phase).  The id
+// row carries 3 null ids in front and null ids behind: phantom ranks count nothing.
+template <int K, bool SMEM>
+__device__ __forceinline__ void class_pass(typename TileMem<SMEM>::addr_t rows, const ClassRef &cr,
+                                           unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
+                                           const PhiloxKey &key, const int *__restrict__ g_always, int (&cnt)[K]) {
+  using TM = TileMem<SMEM>;
+  constexpr int NT = Thr<K>::NT, TS = Thr<K>::TS;
+  const int lane = threadIdx.x & 31;
+  const int o = (int) (n_u & 3ull);
+  const uint32_t Q0 = (uint32_t) (n_u >> 2);
+  const int nsteps = (R2 + o + 127) >> 7;
+  const uint32_t sel = 0x3210u + 0x1111u * (uint32_t) (3 - o);
+  int G[NT];
+#pragma unroll
+  for (int k = 0; k < NT; k++) G[k] = 0;
+  typename TM::addr_t a = rows + 4 * lane;
+  const uint32_t thr_s = cr.thr_s;
+#pragma unroll 2
+  for (int s = 0; s < nsteps; s++) {
+    uint32_t x[4];
+    philox4x32_10(Q0 + (uint32_t) (lane + 32 * s), 0u, gene, chain, key, x);
+    const uint32_t ids = __byte_perm(TM::ld(a), TM::ld(a + 4), sel);
+    a += 128;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t id = __byte_perm(ids, 0u, 0x4440u | (uint32_t) i);
+      uint32_t t[8];
+      Thr<K>::load(thr_s + id * (uint32_t) TS, t);
+#pragma unroll
+      for (int k = 0; k < NT; k++) G[k] += (x[i] > t[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NT; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]) + g_always[k];
+  cnt[0] = R2 - G[0];
+#pragma unroll
+  for (int k = 1; k < NT; k++) cnt[k] = G[k - 1] - G[k];
+  cnt[K - 1] = G[NT - 1];
+}
+
+// -log(lp) of miso_paired.c:409-411 from the plan-wide table (lp is a small positive
+// integer: an isoform length minus a fragment length); anything else is computed.
+__device__ __forceinline__ double neg_log_lp(int lp, const double *__restrict__ neglog, int n_neglog) {
+  if (lp > 0 && lp < n_neglog) return __ldg(neglog + lp);
+  return -log((double) lp);
+}
+
+// ---- the same pass + the read score of the chosen isoforms (paired-end) ---------------
+// Runs before an iteration that records a sample (the MH ratio does not need it,
+// the recorded log score does).  Counts per isoform directly.
+template <int K, bool SMEM, bool WIDE>
+__device__ __noinline__ void class_pass_rp(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
+                                           uint32_t ptab_s, unsigned long long n_u, int R2, uint32_t gene,
+                                           uint32_t chain, const PhiloxKey &key, int paired,
+                                           const int *__restrict__ L, const double *__restrict__ neglog,
+                                           int n_neglog, int *cnt_k, double *rp) {
+  using TM = TileMem<SMEM>;
+  constexpr int NT = Thr<K>::NT, TS = Thr<K>::TS;
+  const int lane = threadIdx.x & 31;
+  const int o = (int) (n_u & 3ull);
+  const uint32_t Q0 = (uint32_t) (n_u >> 2);
+  const int nsteps = (R2 + o + 127) >> 7;
+  int n[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) n[k] = 0;
+  double rp_lane = 0.0;
+  for (int s = 0; s < nsteps; s++) {
+    const int T = lane + 32 * s;
+    uint32_t x[4];
+    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      const int rank = 4 * T - o + i;
+      if (rank < 0 || rank >= R2) continue;
+      const int el = kTilePadFront + rank;
+      const uint32_t id = (TM::ld(rows + (el & ~3)) >> (8 * (el & 3))) & 0xffu;
+      const uint32_t xi = i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3];
+      uint32_t t[8];
+      Thr<K>::load(cr.thr_s + id * (uint32_t) TS, t);
+      const uint32_t meta = lds_u32(cr.meta_s + 4u * id);
+      int chosen = (int) (meta & 0xffu);
+#pragma unroll
+      for (int k = 0; k < NT; k++) chosen += (xi > t[k]);
+#pragma unroll
+      for (int k = 0; k < K; k++) n[k] += (chosen == k);
+      if (paired) {
+        uint32_t cc;
+        if (meta & 0x100u) {
+          const int byte = WIDE ? 2 * el : el;
+          const uint32_t w = TM::ld(rows + ucode_off + (byte & ~3));
+          cc = WIDE ? (w >> (8 * (byte & 2))) & 0xffffu : (w >> (8 * (byte & 3))) & 0xffu;
+        } else {
+          cc = lds_u16(cr.rec_s + 16u * id + 2u * (uint32_t) chosen);
+        }
+        const int lp = __ldg(L + chosen) - ((int) cc - 1);
+        rp_lane += neg_log_lp(lp, neglog, n_neglog) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
+      }
+    }
+  }
+  int mine = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int t = __reduce_add_sync(0xffffffffu, n[k]);
+    if (lane == k) mine = t;
+  }
+  *cnt_k = mine;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
+  *rp = rp_lane;
+}
+
+// ---- the literal rule of miso.c:59-83 on a class tile --------------------------------
+// Codes are rebuilt from the class record (uniform-code classes: the read's own code
+// wherever the record is non-zero).  Used for the final pass of chain 0 (emits the
+// per-read assignment, miso.c:943-946) and for passes thr_update declined.
+template <int K, bool SMEM, bool WIDE>
+__device__ __noinline__ void class_literal(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
+                                           uint32_t ptab_s, double psi_k, unsigned long long n_u, int R2,
+                                           uint32_t gene, uint32_t chain, const PhiloxKey &key, int paired,
+                                           const int *__restrict__ L, const double *__restrict__ neglog,
+                                           int n_neglog, int *cnt_k, double *rp, uint8_t *__restrict__ ass_out) {
+  using TM = TileMem<SMEM>;
+  const int lane = threadIdx.x & 31;
+  const int o = (int) (n_u & 3ull);
+  const uint32_t Q0 = (uint32_t) (n_u >> 2);
+  const int nsteps = (R2 + o + 127) >> 7;
+  double psi[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) psi[k] = shfl_d(psi_k, k);
+  int n[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) n[k] = 0;
+  double rp_lane = 0.0;
+  for (int s = 0; s < nsteps; s++) {
+    const int T = lane + 32 * s;
+    uint32_t x[4];
+    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+      const int rank = 4 * T - o + i;
+      if (rank < 0 || rank >= R2) continue;
+      const int el = kTilePadFront + rank;
+      const uint32_t id = (TM::ld(rows + (el & ~3)) >> (8 * (el & 3))) & 0xffu;
+      const uint32_t meta = lds_u32(cr.meta_s + 4u * id);
+      uint32_t uc = 0;
+      if (meta & 0x100u) {
+        const int byte = WIDE ? 2 * el : el;
+        const uint32_t w = TM::ld(rows + ucode_off + (byte & ~3));
+        uc = WIDE ? (w >> (8 * (byte & 2))) & 0xffffu : (w >> (8 * (byte & 3))) & 0xffu;
+      }
+      const uint32_t xi = i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3];
+      double S = 0.0, C[K];
+      uint32_t code[K];
+      int nv = 0;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const uint32_t idx = lds_u16(cr.rec_s + 16u * id + 2u * k);
+        code[k] = idx == 0u ? 0u : ((meta & 0x100u) ? uc : idx);
+        nv += idx != 0u;
+        S = S + psi[k] * lds_f64(ptab_s + code[k] * 8u);
+        C[k] = S;
+      }
+      const bool two = nv == 2;
+      const double rnd = uniform_from_word(xi) * S;
+      int chosen = -1;
+      uint32_t cc = 0;
+#pragma unroll
+      for (int k = K - 1; k >= 0; k--) {
+        const bool valid = code[k] != 0u;
+        const bool hit = two ? (rnd < C[k]) : (rnd <= C[k]);     // miso.c:71 / :78
+        if (valid && (hit || chosen < 0)) { chosen = k; cc = code[k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < K; k++) n[k] += (chosen == k);
+      if (chosen >= 0 && paired) {
+        const int lp = __ldg(L + chosen) - ((int) cc - 1);
+        rp_lane += neg_log_lp(lp, neglog, n_neglog) + lds_f64(ptab_s + cc * 8u);
+      }
+      if (ass_out) ass_out[rank] = (uint8_t) chosen;
+    }
+  }
+  int mine = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int t = __reduce_add_sync(0xffffffffu, n[k]);
+    if (lane == k) mine = t;
+  }
+  *cnt_k = mine;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
+  *rp = rp_lane;
+}
+
+}  // namespace misob200

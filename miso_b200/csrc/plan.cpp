@@ -15,11 +15,14 @@
 //     src/qsort.c through include/matrix.pmt:579-589).
 #include "plan.hpp"
 
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
+#include <unordered_map>
 
 namespace misob200 {
 
@@ -328,32 +331,119 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   const int R2 = (int) drawn.size();
   h.R2 = R2; d.R2 = R2;
   h.rank_read.assign(drawn.begin(), drawn.end());
-  // code row: 3 pad elements, R2 codes, zero fill to a whole number of 128-read warp
-  // steps plus 16 spare bytes (a lane reads a little past its 4 reads); elements are
-  // bytes, or 16-bit when the insert model has more than 255 fragment lengths.  The
-  // flag row (1 = exactly two compatible isoforms) is always bytes.
+  // ---- weight classes of the drawing reads ------------------------------------
+  // Two reads whose weight vectors (psi_k * p_k)_k are proportional make the same
+  // choice for the same uniform whatever psi is.  Reads whose compatible isoforms all
+  // see the same fragment length (the common case) are proportional to the 0/1
+  // pattern itself: their class key is the pattern, with the ptab index of 1.0
+  // (n_codes, appended on upload) in place of the code.  Other reads key on their
+  // full code vector.  class_kernel.cuh turns each class into K-1 integer thresholds
+  // on the raw Philox word once per iteration.
+  const int one_idx = n_codes;
+  std::vector<uint8_t> cls_id(R2);
+  std::vector<uint16_t> ucode(R2, 0);
+  std::vector<std::array<uint16_t, kMaxIso>> cls_keys;
+  std::vector<int> cls_size;
+  bool class_ok = plan.force_format != 0;
+  if (class_ok) {
+    std::unordered_map<std::string, int> seen;
+    std::string key(2 * kMaxIso, '\0');
+    for (int i = 0; i < R2 && class_ok; i++) {
+      const int32_t *col = codes.data() + (size_t) drawn[i] * K;
+      int32_t common = 0;
+      bool uniform = true;
+      for (int k = 0; k < K; k++) {
+        if (!col[k]) continue;
+        if (!common) common = col[k];
+        else if (col[k] != common) uniform = false;
+      }
+      std::array<uint16_t, kMaxIso> v{};
+      for (int k = 0; k < K; k++) v[k] = (uint16_t) (col[k] ? (uniform ? one_idx : col[k]) : 0);
+      ucode[i] = uniform ? (uint16_t) common : 0;
+      std::memcpy(&key[0], v.data(), 2 * kMaxIso);
+      auto it = seen.find(key);
+      int id;
+      if (it == seen.end()) {
+        id = (int) cls_keys.size();
+        if (id >= kMaxClasses) { class_ok = false; break; }
+        seen.emplace(key, id);
+        cls_keys.push_back(v);
+        cls_size.push_back(0);
+      } else {
+        id = it->second;
+      }
+      cls_id[i] = (uint8_t) id;
+      cls_size[id]++;
+    }
+  }
+
   const int cb = plan.wide ? 2 : 1;
   const int padded = round_up(R2 + kTilePadFront, 128);
-  const int row_bytes = padded * cb + 16;
-  const int flag_row = padded + 16;
-  d.row_bytes = row_bytes;
-  d.flag_off = row_bytes * K;
-  d.tile_bytes = row_bytes * K + flag_row;
-  out.tile.assign((size_t) d.tile_bytes, 0);
-  for (int i = 0; i < R2; i++) {
-    const int32_t *col = codes.data() + (size_t) drawn[i] * K;
-    int nv = 0;
-    for (int k = 0; k < K; k++) {
-      uint8_t *row = out.tile.data() + (size_t) k * row_bytes;
+  if (class_ok) {
+    // class tile: id row (bytes; the padding carries the null class id ncls), uniform-code
+    // row (bytes, or 16-bit when the insert model has more than 255 fragment lengths),
+    // class records: ncls x 8 ptab indices (u16), then ncls meta words
+    // (bits 0-7 first compatible isoform, bit 8 uniform-code class).
+    const int ncls = (int) cls_keys.size();
+    d.format = 1;
+    d.ncls = ncls;
+    d.row_bytes = padded + 16;
+    d.ucode_off = d.row_bytes;
+    d.cls_off = d.ucode_off + padded * cb + 16;
+    d.flag_off = 0;
+    d.tile_bytes = d.cls_off + ncls * 16 + round_up(ncls * 4, 16);
+    out.tile.assign((size_t) d.tile_bytes, 0);
+    std::memset(out.tile.data(), ncls, (size_t) d.row_bytes);
+    uint8_t *uc = out.tile.data() + d.ucode_off;
+    for (int i = 0; i < R2; i++) {
+      out.tile[kTilePadFront + i] = cls_id[i];
       if (plan.wide) {
-        row[2 * (kTilePadFront + i)] = (uint8_t) (col[k] & 0xff);
-        row[2 * (kTilePadFront + i) + 1] = (uint8_t) (col[k] >> 8);
+        uc[2 * (kTilePadFront + i)] = (uint8_t) (ucode[i] & 0xff);
+        uc[2 * (kTilePadFront + i) + 1] = (uint8_t) (ucode[i] >> 8);
       } else {
-        row[kTilePadFront + i] = (uint8_t) col[k];
+        uc[kTilePadFront + i] = (uint8_t) ucode[i];
       }
-      nv += col[k] != 0;
     }
-    out.tile[(size_t) d.flag_off + kTilePadFront + i] = (nv == 2) ? 1 : 0;
+    uint16_t *rec = reinterpret_cast<uint16_t *>(out.tile.data() + d.cls_off);
+    uint32_t *meta = reinterpret_cast<uint32_t *>(out.tile.data() + d.cls_off + ncls * 16);
+    for (int c = 0; c < ncls; c++) {
+      int first = -1;
+      bool uniform = false;
+      for (int k = 0; k < kMaxIso; k++) {
+        rec[c * 8 + k] = cls_keys[c][k];
+        if (cls_keys[c][k] && first < 0) first = k;
+        if (cls_keys[c][k] == one_idx) uniform = true;
+      }
+      meta[c] = (uint32_t) first | (uniform ? 0x100u : 0u);
+      for (int k = 0; k < first; k++) d.g_always[k] += cls_size[c];
+    }
+  } else {
+    // dense tile: per isoform a code row -- 3 pad elements, R2 codes, zero fill to a whole
+    // number of 128-read warp steps plus 16 spare bytes (a lane reads a little past its 4
+    // reads); elements are bytes, or 16-bit when the insert model has more than 255
+    // fragment lengths.  The flag row (1 = exactly two compatible isoforms) is always bytes.
+    const int row_bytes = padded * cb + 16;
+    const int flag_row = padded + 16;
+    d.format = 0;
+    d.row_bytes = row_bytes;
+    d.flag_off = row_bytes * K;
+    d.tile_bytes = row_bytes * K + flag_row;
+    out.tile.assign((size_t) d.tile_bytes, 0);
+    for (int i = 0; i < R2; i++) {
+      const int32_t *col = codes.data() + (size_t) drawn[i] * K;
+      int nv = 0;
+      for (int k = 0; k < K; k++) {
+        uint8_t *row = out.tile.data() + (size_t) k * row_bytes;
+        if (plan.wide) {
+          row[2 * (kTilePadFront + i)] = (uint8_t) (col[k] & 0xff);
+          row[2 * (kTilePadFront + i) + 1] = (uint8_t) (col[k] >> 8);
+        } else {
+          row[kTilePadFront + i] = (uint8_t) col[k];
+        }
+        nv += col[k] != 0;
+      }
+      out.tile[(size_t) d.flag_off + kTilePadFront + i] = (nv == 2) ? 1 : 0;
+    }
   }
   if (plan.keep_match) { h.codes = std::move(codes); h.order = std::move(order); }
 }

@@ -20,6 +20,7 @@ namespace misob200 {
 constexpr int kMaxIso = MISOB200_MAX_ISO;
 constexpr int kMaxCodes = 4096;    // ptab entries that fit the shared-memory table (32 KB)
 constexpr int kTilePadFront = 3;   // bytes in front of rank 0 (stream misalignment, see chain_kernel.cu)
+constexpr int kMaxClasses = 254;   // class ids are bytes; id ncls is the null class of the padding
 
 // Device-visible per-gene descriptor (one per gene, 16-byte aligned, POD).
 struct GeneDesc {
@@ -40,9 +41,17 @@ struct GeneDesc {
   int rp_always;                 // some read score is not finite: keep readProb in every MH ratio
   int status;
   int flag_off;                  // byte offset of the flag row (always u8) inside the tile
-  int tile_bytes;                // K code rows + flag row, multiple of 16
+  int tile_bytes;                // whole tile, multiple of 16
   int pad_[2];
+  // ---- class format (format == 1, class_kernel.cuh) -------------------------
+  int format;                    // 0: dense code rows + flag row; 1: class ids + uniform codes + class records
+  int ncls;                      // weight classes among the drawing reads (<= kMaxClasses)
+  int ucode_off;                 // byte offset of the uniform-code row (u8, or u16 when the plan is "wide")
+  int cls_off;                   // byte offset of the class records (ncls x 8 u16 ptab indices, then ncls u32 meta)
+  int g_always[kMaxIso];         // drawing reads whose first compatible isoform comes after k (their test k
+                                 // is true whatever the uniform: the cumulative sum is still an exact 0)
 };
+static_assert(sizeof(GeneDesc) % 16 == 0, "GeneDesc is copied as a 16-byte aligned POD");
 
 struct GeneHost {
   int K = 0, R = 0, R2 = 0, ncls = 0, status = 0;
@@ -62,6 +71,7 @@ struct Plan {
   int frag_start = 0, frag_len_n = 0;
   std::vector<double> ptab;              // ptab[0] = 0, ptab[j+1] = fragment prob j (SE: {0,1})
   bool wide = false;                     // more than 255 fragment lengths: 16-bit codes
+  int force_format = -1;                 // tests: 0 = dense tiles only, 1 = class tiles whenever possible (default)
   std::vector<GeneDesc> desc;
   std::vector<GeneHost> host;
   std::vector<uint8_t> tiles;            // tile arena, each tile 16-byte aligned

@@ -32,27 +32,33 @@ const char *last_error() { return g_error.c_str(); }
     }                                                                                     \
   } while (0)
 
+constexpr int kBuckets = 2 * (kMaxIso + 1);
+
 struct DevState {
   int device = 0;
   misob200_params_t params{};
   cudaStream_t stream = nullptr;            // copies + summary
-  cudaStream_t kstream[kMaxIso + 1] = {};   // one per K bucket
+  // buckets: b = fmt * (kMaxIso + 1) + K, fmt 0 dense tiles, 1 class tiles
+  cudaStream_t kstream[kBuckets] = {};      // one per bucket
   cudaEvent_t ev[6] = {};
-  cudaEvent_t kdone[kMaxIso + 1] = {};
-  cudaEvent_t kbeg[kMaxIso + 1] = {}, kend[kMaxIso + 1] = {};
+  cudaEvent_t kdone[kBuckets] = {};
+  cudaEvent_t kbeg[kBuckets] = {}, kend[kBuckets] = {};
   uint8_t *d_tiles = nullptr;
   GeneDesc *d_desc = nullptr;
-  double *d_ptab = nullptr;
+  double *d_ptab = nullptr, *d_neglog = nullptr;
+  int n_neglog = 0;
   double *d_samples = nullptr, *d_loglik = nullptr, *d_summary = nullptr;
   uint8_t *d_drawn = nullptr;
   int *d_accrej = nullptr;
   unsigned *d_queue = nullptr;
   int *d_items = nullptr;
-  std::vector<int> items[kMaxIso + 1];
-  int item_off[kMaxIso + 2] = {};
+  std::vector<int> items[kBuckets];
+  int item_off[kBuckets + 1] = {};
   long long n_samples = 0, n_loglik = 0;
   bool uploaded = false, have_run = false;
   bool pinned_tiles = false, pinned_desc = false;
+  std::vector<double> h_ptab;       // plan.ptab + the 1.0 of the uniform-code classes
+  std::vector<double> h_neglog;     // -log(n), read scores of the class format
   std::vector<uint8_t> h_drawn;
   std::vector<int> h_accrej;
   int sm_count = 0;
@@ -95,7 +101,7 @@ void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, l
 static void free_dev(DevState *st) {
   if (!st) return;
   cudaSetDevice(st->device);
-  cudaFree(st->d_tiles); cudaFree(st->d_desc); cudaFree(st->d_ptab); cudaFree(st->d_samples);
+  cudaFree(st->d_tiles); cudaFree(st->d_desc); cudaFree(st->d_ptab); cudaFree(st->d_neglog); cudaFree(st->d_samples);
   cudaFree(st->d_loglik); cudaFree(st->d_summary); cudaFree(st->d_drawn); cudaFree(st->d_accrej);
   cudaFree(st->d_queue); cudaFree(st->d_items);
   for (auto &e : st->ev) if (e) cudaEventDestroy(e);
@@ -152,10 +158,11 @@ static int copy_inputs(Plan &plan, DevState *st) {
   CK(cudaEventRecord(st->ev[0], st->stream));
   if (tile_bytes) CK(cudaMemcpyAsync(st->d_tiles, plan.tiles.data(), tile_bytes, cudaMemcpyHostToDevice, st->stream));
   if (G) CK(cudaMemcpyAsync(st->d_desc, plan.desc.data(), G * sizeof(GeneDesc), cudaMemcpyHostToDevice, st->stream));
-  CK(cudaMemcpyAsync(st->d_ptab, plan.ptab.data(), plan.ptab.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
-  for (int k = 2; k <= kMaxIso; k++)
-    if (!st->items[k].empty())
-      CK(cudaMemcpyAsync(st->d_items + st->item_off[k], st->items[k].data(), st->items[k].size() * sizeof(int),
+  CK(cudaMemcpyAsync(st->d_ptab, st->h_ptab.data(), st->h_ptab.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+  CK(cudaMemcpyAsync(st->d_neglog, st->h_neglog.data(), st->h_neglog.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
+  for (int b = 0; b < kBuckets; b++)
+    if (!st->items[b].empty())
+      CK(cudaMemcpyAsync(st->d_items + st->item_off[b], st->items[b].data(), st->items[b].size() * sizeof(int),
                          cudaMemcpyHostToDevice, st->stream));
   CK(cudaEventRecord(st->ev[1], st->stream));
   CK(cudaStreamSynchronize(st->stream));
@@ -166,7 +173,7 @@ static int copy_inputs(Plan &plan, DevState *st) {
 
 long long input_bytes(const Plan &plan) {
   long long b = (long long) plan.tiles.size() + (long long) plan.desc.size() * (sizeof(GeneDesc) + sizeof(int)) +
-                (long long) plan.ptab.size() * sizeof(double);
+                (long long) (plan.ptab.size() + 1) * sizeof(double);
   return b;
 }
 
@@ -194,40 +201,58 @@ int upload(Plan &plan, const misob200_params_t &p) {
   st->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
   for (auto &e : st->ev) CK(cudaEventCreate(&e));
-  for (int k = 2; k <= kMaxIso; k++) {
-    CK(cudaStreamCreateWithFlags(&st->kstream[k], cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&st->kdone[k], cudaEventDisableTiming));
-    CK(cudaEventCreate(&st->kbeg[k]));
-    CK(cudaEventCreate(&st->kend[k]));
+  for (int b = 0; b < kBuckets; b++) {
+    if (b % (kMaxIso + 1) < 2) continue;
+    CK(cudaStreamCreateWithFlags(&st->kstream[b], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&st->kdone[b], cudaEventDisableTiming));
+    CK(cudaEventCreate(&st->kbeg[b]));
+    CK(cudaEventCreate(&st->kend[b]));
   }
 
   plan_layout(plan, p, &st->n_samples, &st->n_loglik);
   const size_t G = plan.desc.size();
 
-  // work lists: per K, genes ordered by decreasing number of drawing reads
+  // work lists: per (tile format, K), genes ordered by decreasing number of drawing reads
   int total = 0;
-  for (int k = 2; k <= kMaxIso; k++) {
-    auto &v = st->items[k];
-    v.clear();
-    for (size_t g = 0; g < G; g++)
-      if (plan.desc[g].K == k && plan.desc[g].status == 0) v.push_back((int) g);
+  for (int b = 0; b < kBuckets; b++) st->items[b].clear();
+  for (size_t g = 0; g < G; g++) {
+    const GeneDesc &d = plan.desc[g];
+    if (d.status == 0 && d.K >= 2 && d.K <= kMaxIso) st->items[(d.format ? 1 : 0) * (kMaxIso + 1) + d.K].push_back((int) g);
+  }
+  for (int b = 0; b < kBuckets; b++) {
+    auto &v = st->items[b];
     std::stable_sort(v.begin(), v.end(),
                      [&](int a, int b) { return plan.desc[a].R2 > plan.desc[b].R2; });
-    st->item_off[k] = total;
+    st->item_off[b] = total;
     total += (int) v.size();
   }
-  st->item_off[kMaxIso + 1] = total;
+  st->item_off[kBuckets] = total;
+
+  // probability table + the weight 1.0 of the uniform-code classes (index n_codes)
+  st->h_ptab = plan.ptab;
+  st->h_ptab.push_back(1.0);
+  // -log(lp) for the paired-end read scores, lp = L_k - (code - 1) (miso_paired.c:409-411)
+  {
+    int max_l = 0;
+    for (size_t g = 0; g < G; g++)
+      if (plan.desc[g].paired && plan.desc[g].format == 1)
+        for (int k = 0; k < plan.desc[g].K; k++) max_l = std::max(max_l, plan.desc[g].L[k]);
+    st->n_neglog = std::min(max_l + 1, 1 << 21);
+    st->h_neglog.assign(std::max(st->n_neglog, 2), 0.0);
+    for (int n = 1; n < st->n_neglog; n++) st->h_neglog[n] = -std::log((double) n);
+  }
 
   const size_t tile_bytes = plan.tiles.size();
   CK(cudaMalloc(&st->d_tiles, std::max<size_t>(tile_bytes, 16)));
   CK(cudaMalloc(&st->d_desc, std::max<size_t>(G, 1) * sizeof(GeneDesc)));
-  CK(cudaMalloc(&st->d_ptab, plan.ptab.size() * sizeof(double)));
+  CK(cudaMalloc(&st->d_ptab, st->h_ptab.size() * sizeof(double)));
+  CK(cudaMalloc(&st->d_neglog, st->h_neglog.size() * sizeof(double)));
   CK(cudaMalloc(&st->d_samples, std::max<long long>(st->n_samples, 1) * sizeof(double)));
   CK(cudaMalloc(&st->d_loglik, std::max<long long>(st->n_loglik, 1) * sizeof(double)));
   CK(cudaMalloc(&st->d_summary, std::max<size_t>(G, 1) * MISOB200_SUMMARY_F64 * sizeof(double)));
   CK(cudaMalloc(&st->d_drawn, std::max<long long>(plan.n_drawn, 16)));
   CK(cudaMalloc(&st->d_accrej, std::max<size_t>(G, 1) * p.n_chains * 2 * sizeof(int)));
-  CK(cudaMalloc(&st->d_queue, (kMaxIso + 1) * sizeof(unsigned)));
+  CK(cudaMalloc(&st->d_queue, kBuckets * sizeof(unsigned)));
   CK(cudaMalloc(&st->d_items, std::max(total, 1) * sizeof(int)));
 
   // pin the plan's arenas once so the per-run H2D runs at link speed
@@ -242,19 +267,34 @@ int upload(Plan &plan, const misob200_params_t &p) {
   return copy_inputs(plan, st);
 }
 
-template <int K>
+template <int K, int FMT>
 static int launch_bucket(Plan &plan, DevState *st, int *launches) {
-  const auto &v = st->items[K];
+  const int b = FMT * (kMaxIso + 1) + K;
+  const auto &v = st->items[b];
   if (v.empty()) return 0;
   constexpr int WARPS = 4;
-  int slot = 0;
-  for (int g : v) slot = std::max(slot, plan.desc[g].tile_bytes);
-  const int ptab_bytes = ((int) plan.ptab.size() * 8 + 15) & ~15;
-  size_t smem = (size_t) ptab_bytes + WARPS * (16 + (size_t) slot);
+  // per-warp shared memory: the largest tile of the bucket (+ threshold rows, class format)
+  int slot = 0, cls = 0, thr = 0;
+  for (int g : v) {
+    const GeneDesc &d = plan.desc[g];
+    slot = std::max(slot, d.tile_bytes);
+    if (FMT == 1) {
+      cls = std::max(cls, d.tile_bytes - d.cls_off);
+      thr = std::max(thr, ((d.ncls + 1) * Thr<K>::TS + 15) & ~15);
+    }
+  }
+  const int n_ptab = (int) st->h_ptab.size();
+  const int ptab_bytes = (n_ptab * 8 + 15) & ~15;
+  size_t smem = (size_t) ptab_bytes + WARPS * (16 + (size_t) slot + thr);
   const size_t smem_cap = 227 * 1024;
-  if (smem > smem_cap) { slot = 0; smem = (size_t) ptab_bytes + WARPS * 16; }   // stream tiles through L2
-  auto kern = plan.wide ? (slot ? chain_kernel<K, WARPS, true, true> : chain_kernel<K, WARPS, false, true>)
-                        : (slot ? chain_kernel<K, WARPS, true, false> : chain_kernel<K, WARPS, false, false>);
+  bool in_smem = true;
+  if (smem > smem_cap) {      // stream the rows through L2
+    in_smem = false;
+    slot = FMT == 1 ? cls : 0;
+    smem = (size_t) ptab_bytes + WARPS * (16 + (size_t) slot + thr);
+  }
+  auto kern = plan.wide ? (in_smem ? chain_kernel<K, WARPS, true, true, FMT> : chain_kernel<K, WARPS, false, true, FMT>)
+                        : (in_smem ? chain_kernel<K, WARPS, true, false, FMT> : chain_kernel<K, WARPS, false, false, FMT>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -265,26 +305,43 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
 
   ChainParams P;
   P.desc = st->d_desc;
-  P.items = st->d_items + st->item_off[K];
+  P.items = st->d_items + st->item_off[b];
   P.n_genes = (int) v.size();
   P.n_chains = st->params.n_chains;
   P.tiles = st->d_tiles;
   P.ptab = st->d_ptab;
-  P.n_ptab = (int) plan.ptab.size();
+  P.n_ptab = n_ptab;
   P.ptab_min = 1.0;
   for (double v : plan.ptab) if (v > 0 && v < P.ptab_min) P.ptab_min = v;
   P.samples = st->d_samples;
   P.loglik = st->d_loglik;
   P.drawn = st->d_drawn;
   P.accrej = st->d_accrej;
-  P.queue = st->d_queue + K;
+  P.queue = st->d_queue + b;
   P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
   P.start = st->params.start;
   P.key = philox_expand_key(st->params.seed);
   P.slot_bytes = slot;
-  kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[K]>>>(P);
+  P.neglog = st->d_neglog;
+  P.n_neglog = st->n_neglog;
+  P.thr_bytes = thr;
+  kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[b]>>>(P);
   CK(cudaGetLastError());
   (*launches)++;
+  return 0;
+}
+
+template <int FMT>
+static int launch_k(Plan &plan, DevState *st, int k, int *nl) {
+  switch (k) {
+    case 2: return launch_bucket<2, FMT>(plan, st, nl);
+    case 3: return launch_bucket<3, FMT>(plan, st, nl);
+    case 4: return launch_bucket<4, FMT>(plan, st, nl);
+    case 5: return launch_bucket<5, FMT>(plan, st, nl);
+    case 6: return launch_bucket<6, FMT>(plan, st, nl);
+    case 7: return launch_bucket<7, FMT>(plan, st, nl);
+    case 8: return launch_bucket<8, FMT>(plan, st, nl);
+  }
   return 0;
 }
 
@@ -293,32 +350,26 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
   if (!st || !st->uploaded) { set_error("run_resident: plan is not on the device (call misob200_upload)"); return MISOB200_EINVAL; }
   CK(cudaSetDevice(st->device));
   int nl = 0;
-  CK(cudaMemsetAsync(st->d_queue, 0, (kMaxIso + 1) * sizeof(unsigned), st->stream));
+  CK(cudaMemsetAsync(st->d_queue, 0, kBuckets * sizeof(unsigned), st->stream));
   // recorded samples that a short chain never writes stay zero, like the
   // reference's zero-initialised sample matrix
   CK(cudaMemsetAsync(st->d_samples, 0, std::max<long long>(st->n_samples, 1) * sizeof(double), st->stream));
   CK(cudaMemsetAsync(st->d_loglik, 0, std::max<long long>(st->n_loglik, 1) * sizeof(double), st->stream));
   CK(cudaEventRecord(st->ev[2], st->stream));
   int rc = 0;
-  // big-K buckets first: they have the longest chains
-  for (int k = kMaxIso; k >= 2 && !rc; k--) {
-    if (st->items[k].empty()) continue;
-    CK(cudaStreamWaitEvent(st->kstream[k], st->ev[2], 0));
-    CK(cudaEventRecord(st->kbeg[k], st->kstream[k]));
-    switch (k) {
-      case 2: rc = launch_bucket<2>(plan, st, &nl); break;
-      case 3: rc = launch_bucket<3>(plan, st, &nl); break;
-      case 4: rc = launch_bucket<4>(plan, st, &nl); break;
-      case 5: rc = launch_bucket<5>(plan, st, &nl); break;
-      case 6: rc = launch_bucket<6>(plan, st, &nl); break;
-      case 7: rc = launch_bucket<7>(plan, st, &nl); break;
-      case 8: rc = launch_bucket<8>(plan, st, &nl); break;
+  // dense buckets first (slowest per read), big K before small K (longest chains)
+  for (int fmt = 0; fmt < 2 && !rc; fmt++)
+    for (int k = kMaxIso; k >= 2 && !rc; k--) {
+      const int b = fmt * (kMaxIso + 1) + k;
+      if (st->items[b].empty()) continue;
+      CK(cudaStreamWaitEvent(st->kstream[b], st->ev[2], 0));
+      CK(cudaEventRecord(st->kbeg[b], st->kstream[b]));
+      rc = fmt ? launch_k<1>(plan, st, k, &nl) : launch_k<0>(plan, st, k, &nl);
+      if (rc) return rc;
+      CK(cudaEventRecord(st->kend[b], st->kstream[b]));
+      CK(cudaEventRecord(st->kdone[b], st->kstream[b]));
+      CK(cudaStreamWaitEvent(st->stream, st->kdone[b], 0));
     }
-    if (rc) return rc;
-    CK(cudaEventRecord(st->kend[k], st->kstream[k]));
-    CK(cudaEventRecord(st->kdone[k], st->kstream[k]));
-    CK(cudaStreamWaitEvent(st->stream, st->kdone[k], 0));
-  }
   CK(cudaEventRecord(st->ev[3], st->stream));
   CK(cudaStreamSynchronize(st->stream));
   CK(cudaGetLastError());
@@ -591,9 +642,11 @@ int bucket_timing(Plan &plan, double *ms) {
   if (!st || !st->have_run) { set_error("bucket_timing: nothing has run"); return MISOB200_EINVAL; }
   for (int k = 0; k <= kMaxIso; k++) {
     ms[k] = 0.0;
-    if (k >= 2 && !st->items[k].empty()) {
+    for (int fmt = 0; fmt < 2 && k >= 2; fmt++) {
+      const int b = fmt * (kMaxIso + 1) + k;
+      if (st->items[b].empty()) continue;
       float t = 0;
-      if (cudaEventElapsedTime(&t, st->kbeg[k], st->kend[k]) == cudaSuccess) ms[k] = t;
+      if (cudaEventElapsedTime(&t, st->kbeg[b], st->kend[b]) == cudaSuccess) ms[k] = std::max(ms[k], (double) t);
       else cudaGetLastError();
     }
   }

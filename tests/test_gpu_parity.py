@@ -4,7 +4,7 @@ posterior samples and scores to fp64 rounding)."""
 import numpy as np
 import pytest
 
-from helpers import assert_gene_parity, oracle_gene
+from helpers import assert_gene_parity, oracle_gene, simulate_pairs
 
 pytestmark = pytest.mark.gpu
 
@@ -17,10 +17,17 @@ def mb():
     return miso_b200
 
 
+# tile_format -1: class tiles (integer thresholds per weight class, class_pass.cuh);
+# 0: dense tiles (per-read fp64 weights, dense_pass.cuh).  Both must reproduce the oracle.
+FORMATS = [-1, 0]
+
+
+@pytest.mark.parametrize("tile_format", FORMATS)
 @pytest.mark.parametrize("kind,n_genes,reads", [(0, 24, 300), (1, 32, 400)])
-def test_chain_matches_oracle(mb, port, kind, n_genes, reads):
+def test_chain_matches_oracle(mb, port, kind, n_genes, reads, tile_format):
     w = mb.Workload(kind, n_genes, reads, 36, 250.0, 900.0, 4.0, seed=11, first_gene_id=100)
-    plan = mb.Plan().append(w)
+    plan = mb.Plan(tile_format=tile_format).append(w)
+    assert (plan.tile_info()[:, 0] == (1 if tile_format else 0)).all()
     params = mb.make_params(n_iters=600, burn_in=100, lag=5, n_chains=2, seed=77)
     out = plan.run(params)
     assert out["launches"] >= 1
@@ -51,11 +58,12 @@ def test_summary_matches_numpy(mb):
         assert s["accepted"] == r["rundata"][5] and s["rejected"] == r["rundata"][6]
 
 
-def test_wide_insert_model_uses_16_bit_codes(mb, port):
+@pytest.mark.parametrize("tile_format", FORMATS)
+def test_wide_insert_model_uses_16_bit_codes(mb, port, tile_format):
     """sd = 50 -> 401 fragment lengths: codes no longer fit a byte; the 16-bit tile variant
     of the kernel must make the same decisions."""
     w = mb.Workload(1, 20, 500, 36, 300.0, 2500.0, 4.0, seed=13)
-    plan = mb.Plan().append(w)
+    plan = mb.Plan(tile_format=tile_format).append(w)
     fp, fs = plan.fragment_table()
     assert len(fp) > 255
     params = mb.make_params(500, 100, 5, 2, seed=21)
@@ -63,3 +71,44 @@ def test_wide_insert_model_uses_16_bit_codes(mb, port):
     for g in range(20):
         want = oracle_gene(port, w.gene(g), True, params, gene_id=g, pe=(300.0, 2500.0, 4.0))
         assert_gene_parity(plan.gene_result(out, g), want, tag="wide gene %d" % g)
+
+
+def _cassette_batch(mb, n_genes, n_pairs, exon_len, two_cassettes, seed):
+    """Events whose alternative exons are SHORTER than the insert-length window: a pair
+    flanking a cassette exon is compatible with the inclusion and the exclusion isoform at
+    two different fragment lengths, so its weight vector is not a 0/1 pattern and every
+    distinct fragment length is a weight class of its own."""
+    rng = np.random.default_rng(seed)
+    genes, poss, cigs, raw = [], [], [], []
+    for g in range(n_genes):
+        if two_cassettes:
+            exons = ((1, 300), (401, 400 + exon_len), (601, 600 + exon_len + 7), (801, 1100))
+            isoforms = ((0, 1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 3))
+        else:
+            exons = ((1, 300), (401, 400 + exon_len), (601, 900))
+            isoforms = ((0, 1, 2), (0, 2))
+        psi = rng.dirichlet(np.ones(len(isoforms)))
+        pos, cig = simulate_pairs(exons, isoforms, psi, n_pairs, 36, 250.0, 30.0, 4.0, rng)
+        genes.append(mb.Gene(exons, isoforms))
+        poss.append(pos)
+        cigs.append(cig)
+        raw.append((exons, isoforms, pos, cig))
+    rb = mb.ReadBatch(genes, poss, cigs, 36, 1, True, 250.0, 900.0, 4.0)
+    return rb, raw
+
+
+@pytest.mark.parametrize("two_cassettes,want_format", [(False, 1), (True, 0)])
+def test_reads_with_two_fragment_lengths(mb, port, two_cassettes, want_format):
+    """Non-uniform weight classes.  One short cassette exon: up to ~200 classes, still a class
+    tile.  Two: more than 254 classes, the plan must fall back to the dense tile by itself."""
+    rb, raw = _cassette_batch(mb, 10, 1500 if two_cassettes else 700, 61, two_cassettes, seed=5)
+    plan = mb.Plan().append(rb)
+    ti = plan.tile_info()
+    assert (ti[:, 0] == want_format).all(), ti
+    if want_format == 1:
+        assert ti[:, 1].max() > 60          # genuinely many classes, most of them non-uniform
+    params = mb.make_params(n_iters=400, burn_in=100, lag=5, n_chains=2, seed=3)
+    out = plan.run(params)
+    for g, wl_gene in enumerate(raw):
+        want = oracle_gene(port, wl_gene, True, params, gene_id=g)
+        assert_gene_parity(plan.gene_result(out, g), want, tag="cassette gene %d" % g)

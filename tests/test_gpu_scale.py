@@ -15,11 +15,13 @@ def mb():
     return miso_b200
 
 
-def test_tile_too_big_for_shared_memory_streams_from_l2(mb, port):
-    """R = 40k pairs: the tile no longer fits a shared-memory slot, the kernel
-    variant that streams it from global/L2 must make the same decisions."""
-    w = mb.Workload(1, 3, 40000, 36, 250.0, 900.0, 4.0, seed=21)
-    plan = mb.Plan().append(w)
+@pytest.mark.parametrize("tile_format,reads", [(0, 40000), (-1, 120000)])
+def test_tile_too_big_for_shared_memory_streams_from_l2(mb, port, tile_format, reads):
+    """R = 40k pairs (dense tile) / 120k pairs (class tile): the tile no longer fits a
+    shared-memory slot, the kernel variant that streams it from global/L2 must make the
+    same decisions."""
+    w = mb.Workload(1, 3, reads, 36, 250.0, 900.0, 4.0, seed=21)
+    plan = mb.Plan(tile_format=tile_format).append(w)
     params = mb.make_params(60, 10, 5, 2, seed=5)
     out = plan.run(params)
     for g in range(3):

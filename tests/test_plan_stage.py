@@ -95,12 +95,22 @@ def test_edge_cases_and_status_codes():
 
 def test_tile_layout_and_sizes():
     w = mb.Workload(1, 6, 500, 36, 250.0, 900.0, 4.0, seed=9)
-    plan = mb.Plan().append(w)
+    plan = mb.Plan(tile_format=0).append(w)
     G, n_reads, tile_bytes = plan.size()
     info = plan.info()
     assert G == 6 and n_reads == 6 * 500
     want = sum(((int(r2) + 3 + 127) // 128 * 128 + 16) * (int(k) + 1) for k, _, r2, _, _ in info)
     assert tile_bytes == want and tile_bytes % 16 == 0
+    assert (plan.tile_info()[:, 0] == 0).all()
+    # class tiles (the default): an id row and a uniform-code row whatever K is, plus
+    # 16 + 4 bytes per weight class
+    cplan = mb.Plan().append(w)
+    ti = cplan.tile_info()
+    assert (ti[:, 0] == 1).all() and (ti[:, 1] >= 1).all() and (ti[:, 1] <= 254).all()
+    for (k, _, r2, _, _), (_, ncls, tb) in zip(info, ti):
+        padded = (int(r2) + 3 + 127) // 128 * 128
+        assert tb == 2 * (padded + 16) + 16 * ncls + (4 * ncls + 15) // 16 * 16
+    assert cplan.size()[2] == int(ti[:, 2].sum()) < tile_bytes
     p = mb.make_params(1000, 100, 9, 3)
     ns, nl, na = plan.output_sizes(p)
     assert nl == 6 * 3 * 100 and na == n_reads and ns == int((info[:, 0] * 300).sum())
@@ -108,7 +118,7 @@ def test_tile_layout_and_sizes():
 
 def test_wide_insert_model_plan(port):
     w = mb.Workload(1, 6, 300, 36, 300.0, 2500.0, 4.0, seed=13)
-    plan = mb.Plan(keep_match=True).append(w)
+    plan = mb.Plan(keep_match=True, tile_format=0).append(w)
     fp, fs = plan.fragment_table()
     wfp, wfs = port.fragment_table(300.0, 2500.0, 4.0, 36)
     np.testing.assert_array_equal(fp, wfp)
