@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmiso_b200.so")
+# MISOB200_LIB: development only (A/B runs of differently tuned builds on the GPU box)
+LIB_PATH = os.environ.get("MISOB200_LIB") or os.path.join(_HERE, "libmiso_b200.so")
 
 SUCCESS, FAILURE, ENOMEM, EINVAL, UNIMPLEMENTED, ECUDA, ENCCL = 0, 1, 2, 4, 12, 100, 101
 SUMMARY_F64 = 32

@@ -65,52 +65,66 @@ struct ChainParams {
 
 namespace misob200 {
 
-// Everything derived from a candidate alpha (lane i < K-1 holds alpha_i).
+// ---- lane groups ------------------------------------------------------------------
+// The scalar part of an iteration is a long chain of dependent fp64 operations
+// (exp, log, divisions) on K values: lane-distributed, it keeps K <= 8 of the 32 lanes
+// busy.  The warp therefore works on kSpec = 4 PROPOSALS at once: lanes 8g .. 8g+7
+// (group g) evaluate everything that depends only on the proposal of iteration m0+g
+// -- psi, the normalised log psi, the Dirichlet term, both proposal densities --
+// under the assumption that iterations m0 .. m0+g-1 reject (the proposal of an
+// iteration is alpha + sd * z, and alpha only changes on an accept).  Iterations then
+// consume the groups in order; the first accept throws the rest of the batch away.
+// With the 20-40 % acceptance of K >= 3 chains a batch serves ~2.5 iterations for the
+// instruction count of one.  Nothing about the arithmetic changes: every group runs
+// the reference's operations in the reference's order on its own operands.
+constexpr int kSpec = 4;
+
+// Everything derived from a candidate alpha (member i < K-1 of a group holds alpha_i).
 struct Derived {
-  double psi;      // lane k < K     : psi_k             (logit_inv, miso.c:219-241,467)
-  double lp;       // lane k < K     : normalised log psi (score_iso, miso.c:136-149)
-  double q;        // lane i < K-1   : log(psi_i / psi_rest) (mvplogisnorm, miso.c:113)
-  double dir;      // uniform        : ldirichlet (miso.c:165-182)
-  double prod;     // uniform        : 1 / prod(theta) / ltheta (miso.c:110)
+  double psi;      // member k < K    : psi_k             (logit_inv, miso.c:219-241,467)
+  double lp;       // member k < K    : normalised log psi (score_iso, miso.c:136-149)
+  double q;        // member i < K-1  : log(psi_i / psi_rest) (mvplogisnorm, miso.c:113)
+  double dir;      // group-uniform   : ldirichlet (miso.c:165-182)
+  double prod;     // group-uniform   : 1 / prod(theta) / ltheta (miso.c:110)
 };
 
+// gb = first lane of this lane's group, mi = member index (lane - gb)
 template <int K>
 __device__ __forceinline__ Derived derive(double alpha, double offset_k, double hyper_m1_k,
-                                          double lg_sum, double lg_each) {
+                                          double lg_sum, double lg_each, int gb, int mi) {
   constexpr int len = K - 1;
-  const int lane = threadIdx.x & 31;
   Derived r;
-  const double e = exp(alpha);
+  const double e = d_exp(alpha);
   double sumexp = 0.0;
 #pragma unroll
-  for (int i = 0; i < len; i++) sumexp = sumexp + shfl_d(e, i);
+  for (int i = 0; i < len; i++) sumexp = sumexp + shfl_d(e, gb + i);
   sumexp = sumexp + 1.0;
-  double psi = e / sumexp;
+  double psi = d_div(e, sumexp);
   double sumpsi = 0.0;
 #pragma unroll
-  for (int i = 0; i < len; i++) sumpsi = sumpsi + shfl_d(psi, i);
-  if (lane == len) psi = 1 - sumpsi;
+  for (int i = 0; i < len; i++) sumpsi = sumpsi + shfl_d(psi, gb + i);
+  if (mi == len) psi = 1 - sumpsi;
   r.psi = psi;
 
-  const double lg = log(psi);
+  const double lg = d_log(psi);
   const double t = lg + offset_k;
-  double mx = shfl_d(t, 0);
+  double mx = shfl_d(t, gb);
 #pragma unroll
   for (int i = 1; i < K; i++) {
-    const double v = shfl_d(t, i);
+    const double v = shfl_d(t, gb + i);
     if (v > mx) mx = v;
   }
-  const double ex = exp(t - mx);
+  const double ex = d_exp(t - mx);
   double sum = 0.0;
 #pragma unroll
-  for (int i = 0; i < K; i++) sum = sum + shfl_d(ex, i);
-  sum = log(sum) + mx;
+  for (int i = 0; i < K; i++) sum = sum + shfl_d(ex, gb + i);
+  sum = d_log(sum) + mx;
   r.lp = t - sum;
 
   const double term = hyper_m1_k * lg;
   double dir = 0.0;
 #pragma unroll
-  for (int i = 0; i < K; i++) dir = dir + shfl_d(term, i);
+  for (int i = 0; i < K; i++) dir = dir + shfl_d(term, gb + i);
   dir = dir + lg_sum;
   dir = dir - lg_each;
   r.dir = dir;
@@ -118,22 +132,23 @@ __device__ __forceinline__ Derived derive(double alpha, double offset_k, double 
   double lth = 1.0, prod = 1.0;
 #pragma unroll
   for (int i = 0; i < len; i++) {
-    const double at = shfl_d(psi, i);
+    const double at = shfl_d(psi, gb + i);
     lth = lth - at;
     prod = prod * at;
   }
-  r.prod = 1.0 / prod / lth;
-  r.q = log(psi / lth);
+  r.prod = d_div(d_div(1.0, prod), lth);
+  r.q = d_log(d_div(psi, lth));
   return r;
 }
 
-// sum_k n_k * v_k in isoform order, skipping isoforms nothing is assigned to
+// sum_k n_k * v_k in isoform order within the lane's group, skipping isoforms nothing
+// is assigned to
 template <int K>
-__device__ __forceinline__ double count_dot(int cnt_k, double v_k) {
+__device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb) {
   const double a = cnt_k ? (double) cnt_k * v_k : 0.0;
   double s = 0.0;
 #pragma unroll
-  for (int i = 0; i < K; i++) s = s + shfl_d(a, i);
+  for (int i = 0; i < K; i++) s = s + shfl_d(a, gb + i);
   return s;
 }
 
@@ -142,7 +157,8 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
                           typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s, const ClassRef &cr) {
   constexpr int len = K - 1;
   const int lane = threadIdx.x & 31;
-  const int kk = lane < K ? lane : K - 1;
+  const int gb = lane & 24, mi = lane & 7, grp = lane >> 3;
+  const int kk = mi < K ? mi : K - 1;
   const double offset_k = d.offset[kk];
   const double hyper_m1_k = d.hyper_m1[kk];
   const double rs_se_k = d.rs_se[kk];
@@ -161,7 +177,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
 
   unsigned long long n_u = 0;
   // ---- start state, splicing_drift_proposal_init (miso.c:330-447) ----------
-  double alpha;
+  double alpha;            // replicated in every group: member i < K-1 holds alpha_i
   if (P.start == MISOB200_START_AUTO) {
     if (K == 2) { n_u = 1; alpha = 0.0; }     // one uniform drawn and discarded (miso.c:365)
     else alpha = 1.0 / (K - 1);
@@ -169,22 +185,18 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     alpha = 0.0;
   }
 
-  // normals are produced 32 at a time (lane l holds normal zbase + l)
-  uint32_t zbase = 0xffffff00u;           // forces a refill on first use
-  double zbuf = 0.0;
-  auto next_normals = [&](uint32_t first) -> double {   // lane i < len gets normal first + i
-    if (first - zbase + (uint32_t) len > 32u) {
-      zbase = first;
-      zbuf = stream_normal(first + (uint32_t) lane, gid, (uint32_t) chain, key);
-    }
-    return shfl_d(zbuf, (int) ((first - zbase + (uint32_t) lane) & 31u));
-  };
+  // normals are produced 32 at a time into a 64-entry window (lane l holds normals
+  // zbase + l and zbase + 32 + l); iteration m consumes normals (m+1)*len .. +len-1
+  // (miso.c:851 -> :192-196), a batch looks kSpec iterations ahead
+  uint32_t zbase = 0u;
+  double zbuf0 = stream_normal((uint32_t) lane, gid, (uint32_t) chain, key);
+  double zbuf1 = stream_normal(32u + (uint32_t) lane, gid, (uint32_t) chain, key);
 
-  Derived cur;
+  Derived cur;             // replicated in every group
   cur.psi = cur.lp = cur.q = cur.dir = cur.prod = 0.0;
   double psi_r[K];
   int cnt[K];
-  int cnt_k;               // lane k: reads currently assigned to isoform k
+  int cnt_k = 0;           // member k: reads currently assigned to isoform k (every group)
   double rp_drawn = 0.0;
   int lagc = 0, n_rec = 0, acc = 0, rej = 0;
   const int S_total = (P.n_iters - P.burn_in) / P.lag;
@@ -204,6 +216,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
       }
       ok = !ok && (pmin * P.ptab_min >= 1e-290);        // fast rule valid for every read of this pass
     }
+    int c = 0;             // member k: drawing reads assigned to isoform k
     if (FMT == 0) {
       if (ok) {
         if (rec_next && !last)
@@ -212,69 +225,92 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
         else
           reassign_pass<K, 0, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, psi_r, n_u, R2, gid, (uint32_t) chain, key, paired, L,
                                     cnt, rp_drawn);
-        int c = 0;
 #pragma unroll
-        for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
-        cnt_k = c + nfix_k;
-      }
-      if (!ok) {   // final pass of chain 0, or a read whose weights underflow: literal rule
-        int c = 0;
+        for (int k = 0; k < K; k++) c = (mi == k) ? cnt[k] : c;
+      } else {     // final pass of chain 0, or a read whose weights underflow: literal rule
         reassign_literal<K, SMEM, WIDE>(rows, row_bytes, flag_off, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired,
                                   L, &c, &rp_drawn, last ? ass_out : nullptr);
-        cnt_k = c + nfix_k;
       }
     } else {
       if (ok && thr_state == 0) thr_state = thr_update<K>(cr, ptab_s, psi_r) ? 2 : 1;
       ok = ok && thr_state == 1;
-      int c = 0;
-      if (ok && !(rec_next && !last)) {
+      if (ok && !(rec_next && !last && paired)) {
         class_pass<K, SMEM>(rows, cr, n_u, R2, gid, (uint32_t) chain, key, g_always, cnt);
 #pragma unroll
-        for (int k = 0; k < K; k++) c = (lane == k) ? cnt[k] : c;
+        for (int k = 0; k < K; k++) c = (mi == k) ? cnt[k] : c;
       } else if (ok) {
-        class_pass_rp<K, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gid, (uint32_t) chain, key, paired, L,
+        // (only paired-end passes get here with a read score to compute; see rec_next)
+        class_pass_rp<K, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gid, (uint32_t) chain, key, g_always,
                                      P.neglog, P.n_neglog, &c, &rp_drawn);
       } else {     // final pass of chain 0, thresholds declined, or weights that underflow
         class_literal<K, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired, L,
                                      P.neglog, P.n_neglog, &c, &rp_drawn, last ? ass_out : nullptr);
       }
-      cnt_k = c + nfix_k;
     }
+    cnt_k = c + nfix_k;
     n_u += (unsigned long long) R2;
     return rec_next || !ok;
   };
 
   bool have_rp = false;
 
+  // the batch: group g holds the proposal of iteration m0 + g, valid while no iteration
+  // from m0 on has accepted
+  int m0 = 0;
+  bool batch_ok = false;
+  double alphaB = 0.0, scP = 0.0, scC = 0.0;
+  Derived nwB;
+  nwB.psi = nwB.lp = nwB.q = nwB.dir = nwB.prod = 0.0;
+
+  auto make_batch = [&](int m) {
+    m0 = m;
+    batch_ok = true;
+    // ---- propose (miso.c:851): alphaNew = alpha + sd * N(0,1), group g for iteration m + g
+    const uint32_t first = (uint32_t) (m + 1) * (uint32_t) len;
+    while (first - zbase >= 32u) {         // slide the window (first grows by len < 32 per iteration)
+      zbase += 32u;
+      zbuf0 = zbuf1;
+      zbuf1 = stream_normal(zbase + 32u + (uint32_t) lane, gid, (uint32_t) chain, key);
+    }
+    const uint32_t zi = first - zbase + (uint32_t) (grp * len + (mi < len ? mi : 0));     // < 32 + kSpec * len <= 60
+    const double za = shfl_d(zbuf0, (int) (zi & 31u)), zb = shfl_d(zbuf1, (int) (zi & 31u));
+    const double z = zi < 32u ? za : zb;
+    alphaB = alpha + sd * z;
+    nwB = derive<K>(alphaB, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
+    // ---- proposal densities (miso.c:531-534, :97-122): member 0 evaluates the density of
+    // the current point seen from the proposal, member 1 the reverse
+    const double t1 = cur.q - alphaB;                        // theta = psi,    mu = alphaNew
+    const double t2 = nwB.q - alpha;                         // theta = psiNew, mu = alpha
+    const double e1 = d_div((-0.5) * t1 * t1, sigma), e2 = d_div((-0.5) * t2 * t2, sigma);
+    double ep1 = 0.0, ep2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < len; i++) { ep1 = ep1 + shfl_d(e1, gb + i); ep2 = ep2 + shfl_d(e2, gb + i); }
+    const double xe = d_exp(mi == 0 ? ep1 : ep2);
+    const double pdf = covar * (mi == 0 ? cur.prod : nwB.prod) * xe;
+    const double sc = d_log(pdf);
+    scP = shfl_d(sc, gb);            // ptoCS
+    scC = shfl_d(sc, gb + 1);        // ctoPS
+  };
+
   // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed
   // by the initial assignment (miso.c:840-843); m >= 0 are the iterations proper.
   for (int m = -1; m < P.n_iters; m++) {
-    // ---- propose (miso.c:851) --------------------------------------------
-    const double alphaN = alpha + sd * next_normals((uint32_t) (m + 1) * (uint32_t) len);
-    const Derived nw = derive<K>(alphaN, offset_k, hyper_m1_k, lg_sum, lg_each);
+    if (!batch_ok || m - m0 >= kSpec) make_batch(m);
+    const int src = 8 * (m - m0) + mi;          // this member in the group of iteration m
     if (m < 0) {
-      alpha = alphaN; cur = nw; thr_state = 0;
+      alpha = shfl_d(alphaB, src);
+      cur.psi = shfl_d(nwB.psi, src); cur.lp = shfl_d(nwB.lp, src); cur.q = shfl_d(nwB.q, src);
+      cur.dir = shfl_d(nwB.dir, src); cur.prod = shfl_d(nwB.prod, src);
+      batch_ok = false; thr_state = 0;
     } else {
-    // ---- joint scores (miso.c:524-529) -----------------------------------
+    // ---- joint scores (miso.c:524-529); every group scores its own proposal --------
     double rp;
-    if (!paired) rp = count_dot<K>(cnt_k, rs_se_k);          // sum_r isoscores[ass_r], miso.c:267-271
+    if (!paired) rp = count_dot<K>(cnt_k, rs_se_k, gb);      // sum_r isoscores[ass_r], miso.c:267-271
     else rp = have_rp ? d.rp_fixed + rp_drawn : 0.0;        // cancels in the ratio when not recorded
-    const double ppJS = rp + count_dot<K>(cnt_k, nw.lp) + nw.dir;
-    const double pcJS = rp + count_dot<K>(cnt_k, cur.lp) + cur.dir;
-
-    // ---- proposal densities (miso.c:531-534, :97-122) --------------------
-    const double t1 = cur.q - alphaN;                        // theta = psi,    mu = alphaNew
-    const double t2 = nw.q - alpha;                          // theta = psiNew, mu = alpha
-    const double e1 = (-0.5) * t1 * t1 / sigma, e2 = (-0.5) * t2 * t2 / sigma;
-    double ep1 = 0.0, ep2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < len; i++) { ep1 = ep1 + shfl_d(e1, i); ep2 = ep2 + shfl_d(e2, i); }
-    const double xe = exp(lane == 0 ? ep1 : ep2);
-    const double pdf = covar * (lane == 0 ? cur.prod : nw.prod) * xe;
-    const double sc = log(pdf);
-    const double ptoCS = shfl_d(sc, 0), ctoPS = shfl_d(sc, 1);
-
-    const double acceptP = (m > 0) ? exp(ppJS + ptoCS - (pcJS + ctoPS)) : exp(ppJS - pcJS);
+    const double ppJS_g = rp + count_dot<K>(cnt_k, nwB.lp, gb) + nwB.dir;
+    const double pcJS = rp + count_dot<K>(cnt_k, cur.lp, gb) + cur.dir;
+    const double acceptP_g = d_exp((m > 0) ? ppJS_g + scP - (pcJS + scC) : ppJS_g - pcJS);
+    const double acceptP = shfl_d(acceptP_g, src & 24);
 
     // ---- accept (miso.c:869-880): the uniform is drawn only if acceptP < 1 --
     bool accept = acceptP >= 1;
@@ -285,7 +321,11 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     }
     double cJS = pcJS;
     if (accept) {
-      alpha = alphaN; cur = nw; cJS = ppJS; acc++; thr_state = 0;
+      cJS = shfl_d(ppJS_g, src & 24);
+      alpha = shfl_d(alphaB, src);
+      cur.psi = shfl_d(nwB.psi, src); cur.lp = shfl_d(nwB.lp, src); cur.q = shfl_d(nwB.q, src);
+      cur.dir = shfl_d(nwB.dir, src); cur.prod = shfl_d(nwB.prod, src);
+      acc++; thr_state = 0; batch_ok = false;
     } else {
       rej++;
     }
@@ -320,8 +360,11 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
 // Shared memory: [ptab | per warp {mbarrier (16 B), slot, threshold rows (FMT 1)}].  The slot
 // holds the gene's whole tile (SMEM), or only its class records when the rows are streamed
 // from global/L2 (FMT 1, !SMEM).
+#ifndef MISOB200_MINBLOCKS_CLASS
+#define MISOB200_MINBLOCKS_CLASS 4
+#endif
 template <int K, int WARPS, bool SMEM, bool WIDE, int FMT>
-__global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? MISOB200_MINBLOCKS_CLASS : (K <= 6 ? 4 : 3))) chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *s_ptab = reinterpret_cast<double *>(smem);
@@ -348,7 +391,8 @@ __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(con
     const uint32_t tile_bytes = (uint32_t) d.tile_bytes;
     ClassRef cr;
     cr.ncls = FMT == 1 ? d.ncls : 0;
-    cr.thr_s = smem_u32(slot + P.slot_bytes);
+    cr.thr_s = smem_u32(slot + P.slot_bytes) + 32u;
+    cr.l_s = smem_u32(slot + P.slot_bytes);
     cr.rec_s = smem_u32(slot) + (SMEM ? (uint32_t) d.cls_off : 0u);
     cr.meta_s = cr.rec_s + 16u * (uint32_t) cr.ncls;
     __syncwarp();
@@ -364,10 +408,11 @@ __global__ void __launch_bounds__(WARPS * 32, (K <= 6 ? 4 : 3)) chain_kernel(con
       const int n16 = (int) (tile_bytes - (uint32_t) d.cls_off) >> 4;
       for (int i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(slot)[i] = __ldg(src + i);
     }
+    if (FMT == 1 && lane < kMaxIso) reinterpret_cast<int *>(slot + P.slot_bytes)[lane] = d.L[lane];
     if (FMT == 1 && lane == 0) {      // null class of the padding: no test is ever true
       uint32_t never[8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) never[k] = 0xffffffffu;
+      for (int k = 0; k < 8; k++) never[k] = 0u;        // rows hold ~t_k
       Thr<K>::store(cr.thr_s + (uint32_t) (Thr<K>::TS * cr.ncls), never);
     }
     if (SMEM) {

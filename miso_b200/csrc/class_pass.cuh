@@ -76,8 +76,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
 // Shared-memory addresses of a gene's class data (all per warp).
 struct ClassRef {
   uint32_t rec_s;    // ncls x 8 u16 ptab indices (0 = incompatible)
-  uint32_t meta_s;   // ncls x u32: bits 0-7 first compatible isoform, bit 8 uniform-code class
-  uint32_t thr_s;    // (ncls + 1) x Thr<K>::TS bytes, row ncls = null class (no test ever true)
+  uint32_t meta_s;   // (ncls + 1) x u32: bits 0-7 first compatible isoform, bit 8 uniform-code class
+  uint32_t thr_s;    // (ncls + 1) x Thr<K>::TS bytes of ~t_k, row ncls = null class (all 0: no test ever true)
+  uint32_t l_s;      // 8 ints: L_k of the paired-end read score, lp = L_k - (code - 1) (miso_paired.c:409-410)
   int ncls;
 };
 
@@ -101,10 +102,10 @@ __device__ __forceinline__ bool thr_update(const ClassRef &cr, uint32_t ptab_s, 
       S = S + psi[k] * lds_f64(ptab_s + idx * 8u);      // CUMSUM, miso_paired.c:11-22
       C[k] = S;
     }
-    const double inv = 4294967296.0 / S;
-    uint32_t t[8];
+    const double inv = d_div(4294967296.0, S);
+    uint32_t t[8];                 // stored complemented: w > t  <=>  w + ~t carries out of 32 bits
 #pragma unroll
-    for (int k = 0; k < 8; k++) t[k] = 0xffffffffu;
+    for (int k = 0; k < 8; k++) t[k] = 0u;
 #pragma unroll
     for (int k = 0; k < NT; k++) {
       const double tau = C[k] * inv - 0.5;
@@ -114,7 +115,7 @@ __device__ __forceinline__ bool thr_update(const ClassRef &cr, uint32_t ptab_s, 
       // isoforms before the first compatible one: C_k is an exact 0 < rnd, the test is
       // always true; those reads are counted by GeneDesc.g_always, the row says "never"
       if (k >= first) {
-        t[k] = tk;
+        t[k] = ~tk;
         bad = bad || !good;
       }
     }
@@ -125,15 +126,29 @@ __device__ __forceinline__ bool thr_update(const ClassRef &cr, uint32_t ptab_s, 
   return bad;
 }
 
-// ---- one reassignment pass, counts only -----------------------------------------
+// -log(lp) of miso_paired.c:409-411 from the plan-wide table (lp is a small positive
+// integer: an isoform length minus a fragment length); anything else is computed.
+__device__ __forceinline__ double neg_log_lp(int lp, const double *__restrict__ neglog, int n_neglog) {
+  if (lp > 0 && lp < n_neglog) return __ldg(neglog + lp);
+  return -d_log((double) lp);
+}
+
+// ---- one reassignment pass ---------------------------------------------------------
 // Lane handles Philox block Q0+T (uniform indices 4(Q0+T)..+3), T = lane + 32*step,
 // i.e. ranks 4T-o .. 4T-o+3 with o = n_u & 3 (the stream is sequential and the accept
 // draw is conditional, miso.c:870, so a pass starts at an arbitrary phase).  The id
 // row carries 3 null ids in front and null ids behind: phantom ranks count nothing.
-template <int K, bool SMEM>
-__device__ __forceinline__ void class_pass(typename TileMem<SMEM>::addr_t rows, const ClassRef &cr,
-                                           unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
-                                           const PhiloxKey &key, const int *__restrict__ g_always, int (&cnt)[K]) {
+//   MODE 0: counts only.
+//   MODE 1: + the read score of the chosen isoforms (paired-end, miso_paired.c:157-163);
+//           runs before an iteration that records a sample (the MH ratio does not need
+//           the read score, the recorded log score does).
+template <int K, int MODE, bool SMEM, bool WIDE>
+__device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
+                                                uint32_t ptab_s, unsigned long long n_u, int R2, uint32_t gene,
+                                                uint32_t chain, const PhiloxKey &key,
+                                                const int *__restrict__ g_always,
+                                                const double *__restrict__ neglog, int n_neglog,
+                                                int (&cnt)[K], double &rp) {
   using TM = TileMem<SMEM>;
   constexpr int NT = Thr<K>::NT, TS = Thr<K>::TS;
   const int lane = threadIdx.x & 31;
@@ -141,103 +156,96 @@ __device__ __forceinline__ void class_pass(typename TileMem<SMEM>::addr_t rows, 
   const uint32_t Q0 = (uint32_t) (n_u >> 2);
   const int nsteps = (R2 + o + 127) >> 7;
   const uint32_t sel = 0x3210u + 0x1111u * (uint32_t) (3 - o);
-  int G[NT];
+  uint32_t G[NT];
 #pragma unroll
   for (int k = 0; k < NT; k++) G[k] = 0;
   typename TM::addr_t a = rows + 4 * lane;
+  typename TM::addr_t ua = rows + ucode_off + (WIDE ? 8 : 4) * lane;
+  const int hs = 3 - o;                               // 16-bit codes: halfwords into the 8-halfword window
+  const bool hb = (hs >> 1) != 0;
+  const uint32_t hsh = 16u * (uint32_t) (hs & 1);
   const uint32_t thr_s = cr.thr_s;
-#pragma unroll 2
+  const uint32_t ncls = (uint32_t) cr.ncls;
+  double rp_lane = 0.0;
+  uint32_t tot = 0;                                   // MODE 1: sum of the G_k so far
+#pragma unroll (MODE == 0 ? 2 : 1)
   for (int s = 0; s < nsteps; s++) {
     uint32_t x[4];
     philox4x32_10(Q0 + (uint32_t) (lane + 32 * s), 0u, gene, chain, key, x);
     const uint32_t ids = __byte_perm(TM::ld(a), TM::ld(a + 4), sel);
     a += 128;
+    uint32_t uc01 = 0, uc23 = 0;                      // MODE 1: the 4 reads' own codes
+    if (MODE == 1) {
+      if (!WIDE) {
+        uc01 = __byte_perm(TM::ld(ua), TM::ld(ua + 4), sel);
+      } else {
+        const uint4 w = TM::ld4(ua);
+        const uint32_t wa = hb ? w.y : w.x, wb = hb ? w.z : w.y, wc = hb ? w.w : w.z;
+        uc01 = __funnelshift_r(wa, wb, hsh);
+        uc23 = __funnelshift_r(wb, wc, hsh);
+      }
+      ua += WIDE ? 256 : 128;
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const uint32_t id = __byte_perm(ids, 0u, 0x4440u | (uint32_t) i);
-      uint32_t t[8];
-      Thr<K>::load(thr_s + id * (uint32_t) TS, t);
+      uint32_t nt[8];
+      Thr<K>::load(thr_s + id * (uint32_t) TS, nt);
 #pragma unroll
-      for (int k = 0; k < NT; k++) G[k] += (x[i] > t[k]);
-    }
-  }
+      for (int k = 0; k < NT; k++)      // G_k += (w > t_k): carry out of w + ~t_k, added with carry
+        asm("{\n\t.reg .u32 j;\n\tadd.cc.u32 j, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(G[k]) : "r"(x[i]), "r"(nt[k]));
+      if (MODE == 1) {
+        uint32_t now = 0;
 #pragma unroll
-  for (int k = 0; k < NT; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]) + g_always[k];
-  cnt[0] = R2 - G[0];
-#pragma unroll
-  for (int k = 1; k < NT; k++) cnt[k] = G[k - 1] - G[k];
-  cnt[K - 1] = G[NT - 1];
-}
-
-// -log(lp) of miso_paired.c:409-411 from the plan-wide table (lp is a small positive
-// integer: an isoform length minus a fragment length); anything else is computed.
-__device__ __forceinline__ double neg_log_lp(int lp, const double *__restrict__ neglog, int n_neglog) {
-  if (lp > 0 && lp < n_neglog) return __ldg(neglog + lp);
-  return -log((double) lp);
-}
-
-// ---- the same pass + the read score of the chosen isoforms (paired-end) ---------------
-// Runs before an iteration that records a sample (the MH ratio does not need it,
-// the recorded log score does).  Counts per isoform directly.
-template <int K, bool SMEM, bool WIDE>
-__device__ __noinline__ void class_pass_rp(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
-                                           uint32_t ptab_s, unsigned long long n_u, int R2, uint32_t gene,
-                                           uint32_t chain, const PhiloxKey &key, int paired,
-                                           const int *__restrict__ L, const double *__restrict__ neglog,
-                                           int n_neglog, int *cnt_k, double *rp) {
-  using TM = TileMem<SMEM>;
-  constexpr int NT = Thr<K>::NT, TS = Thr<K>::TS;
-  const int lane = threadIdx.x & 31;
-  const int o = (int) (n_u & 3ull);
-  const uint32_t Q0 = (uint32_t) (n_u >> 2);
-  const int nsteps = (R2 + o + 127) >> 7;
-  int n[K];
-#pragma unroll
-  for (int k = 0; k < K; k++) n[k] = 0;
-  double rp_lane = 0.0;
-  for (int s = 0; s < nsteps; s++) {
-    const int T = lane + 32 * s;
-    uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
-#pragma unroll 1
-    for (int i = 0; i < 4; i++) {
-      const int rank = 4 * T - o + i;
-      if (rank < 0 || rank >= R2) continue;
-      const int el = kTilePadFront + rank;
-      const uint32_t id = (TM::ld(rows + (el & ~3)) >> (8 * (el & 3))) & 0xffu;
-      const uint32_t xi = i == 0 ? x[0] : i == 1 ? x[1] : i == 2 ? x[2] : x[3];
-      uint32_t t[8];
-      Thr<K>::load(cr.thr_s + id * (uint32_t) TS, t);
-      const uint32_t meta = lds_u32(cr.meta_s + 4u * id);
-      int chosen = (int) (meta & 0xffu);
-#pragma unroll
-      for (int k = 0; k < NT; k++) chosen += (xi > t[k]);
-#pragma unroll
-      for (int k = 0; k < K; k++) n[k] += (chosen == k);
-      if (paired) {
+        for (int k = 0; k < NT; k++) now += G[k];
+        const uint32_t meta = lds_u32(cr.meta_s + 4u * id);
+        const uint32_t chosen = (meta & 0xffu) + (now - tot);       // first compatible + tests passed
+        tot = now;
         uint32_t cc;
-        if (meta & 0x100u) {
-          const int byte = WIDE ? 2 * el : el;
-          const uint32_t w = TM::ld(rows + ucode_off + (byte & ~3));
-          cc = WIDE ? (w >> (8 * (byte & 2))) & 0xffffu : (w >> (8 * (byte & 3))) & 0xffu;
-        } else {
-          cc = lds_u16(cr.rec_s + 16u * id + 2u * (uint32_t) chosen);
-        }
-        const int lp = __ldg(L + chosen) - ((int) cc - 1);
-        rp_lane += neg_log_lp(lp, neglog, n_neglog) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
+        if (!WIDE) cc = __byte_perm(uc01, 0u, 0x4440u | (uint32_t) i);
+        else cc = __byte_perm(i < 2 ? uc01 : uc23, 0u, (i & 1) ? 0x4432u : 0x4410u);
+        if (!(meta & 0x100u)) cc = lds_u16(cr.rec_s + 16u * id + 2u * chosen);   // not a uniform-code class
+        const int lp = (int) lds_u32(cr.l_s + 4u * chosen) - ((int) cc - 1);
+        const double sc = neg_log_lp(lp, neglog, n_neglog) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
+        if (id != ncls) rp_lane += sc;
       }
     }
   }
-  int mine = 0;
 #pragma unroll
-  for (int k = 0; k < K; k++) {
-    const int t = __reduce_add_sync(0xffffffffu, n[k]);
-    if (lane == k) mine = t;
+  for (int k = 0; k < NT; k++) G[k] = __reduce_add_sync(0xffffffffu, G[k]) + (uint32_t) g_always[k];
+  cnt[0] = R2 - (int) G[0];
+#pragma unroll
+  for (int k = 1; k < NT; k++) cnt[k] = (int) (G[k - 1] - G[k]);
+  cnt[K - 1] = (int) G[NT - 1];
+  if (MODE == 1) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
+    rp = rp_lane;
   }
-  *cnt_k = mine;
+}
+
+template <int K, bool SMEM>
+__device__ __forceinline__ void class_pass(typename TileMem<SMEM>::addr_t rows, const ClassRef &cr,
+                                           unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
+                                           const PhiloxKey &key, const int *__restrict__ g_always, int (&cnt)[K]) {
+  double unused;
+  class_pass_body<K, 0, SMEM, false>(rows, 0, cr, 0u, n_u, R2, gene, chain, key, g_always, nullptr, 0, cnt, unused);
+}
+
+// MODE 1 out of line: one pass in `lag` runs it
+template <int K, bool SMEM, bool WIDE>
+__device__ __noinline__ void class_pass_rp(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
+                                           uint32_t ptab_s, unsigned long long n_u, int R2, uint32_t gene,
+                                           uint32_t chain, const PhiloxKey &key, const int *__restrict__ g_always,
+                                           const double *__restrict__ neglog, int n_neglog, int *cnt_k, double *rp) {
+  int cnt[K];
+  class_pass_body<K, 1, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gene, chain, key, g_always, neglog, n_neglog,
+                                    cnt, *rp);
+  const int lane = threadIdx.x & 31;
+  int c = 0;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
-  *rp = rp_lane;
+  for (int k = 0; k < K; k++) c = ((lane & 7) == k) ? cnt[k] : c;
+  *cnt_k = c;
 }
 
 // ---- the literal rule of miso.c:59-83 on a class tile --------------------------------
@@ -314,7 +322,7 @@ __device__ __noinline__ void class_literal(typename TileMem<SMEM>::addr_t rows, 
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const int t = __reduce_add_sync(0xffffffffu, n[k]);
-    if (lane == k) mine = t;
+    if ((lane & 7) == k) mine = t;        // member k of every lane group
   }
   *cnt_k = mine;
 #pragma unroll

@@ -204,7 +204,7 @@ __device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t row
 #pragma unroll
   for (int k = 0; k < K; k++) {
     const int t = __reduce_add_sync(0xffffffffu, n[k]);
-    if (lane == k) mine = t;
+    if ((lane & 7) == k) mine = t;        // member k of every lane group
   }
   *cnt_k = mine;
 #pragma unroll

@@ -64,7 +64,7 @@ __device__ __forceinline__ double stream_uniform(unsigned long long n, uint32_t 
   return uniform_from_word(w);
 }
 
-__device__ __forceinline__ double stream_normal(uint32_t n, uint32_t gene, uint32_t chain,
+__device__ __noinline__ double stream_normal(uint32_t n, uint32_t gene, uint32_t chain,
                                                 const PhiloxKey &key) {
   uint32_t x[4];
   philox4x32_10(n, 1u, gene, chain, key, x);

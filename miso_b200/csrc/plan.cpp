@@ -383,7 +383,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
     // class tile: id row (bytes; the padding carries the null class id ncls), uniform-code
     // row (bytes, or 16-bit when the insert model has more than 255 fragment lengths),
     // class records: ncls x 8 ptab indices (u16), then ncls meta words
-    // (bits 0-7 first compatible isoform, bit 8 uniform-code class).
+    // (bits 0-7 first compatible isoform, bit 8 uniform-code class), one more for the null class.
     const int ncls = (int) cls_keys.size();
     d.format = 1;
     d.ncls = ncls;
@@ -391,7 +391,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
     d.ucode_off = d.row_bytes;
     d.cls_off = d.ucode_off + padded * cb + 16;
     d.flag_off = 0;
-    d.tile_bytes = d.cls_off + ncls * 16 + round_up(ncls * 4, 16);
+    d.tile_bytes = d.cls_off + ncls * 16 + round_up((ncls + 1) * 4, 16);
     out.tile.assign((size_t) d.tile_bytes, 0);
     std::memset(out.tile.data(), ncls, (size_t) d.row_bytes);
     uint8_t *uc = out.tile.data() + d.ucode_off;
@@ -417,6 +417,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
       meta[c] = (uint32_t) first | (uniform ? 0x100u : 0u);
       for (int k = 0; k < first; k++) d.g_always[k] += cls_size[c];
     }
+    meta[ncls] = 0x100u;      // null class of the padding
   } else {
     // dense tile: per isoform a code row -- 3 pad elements, R2 codes, zero fill to a whole
     // number of 128-read warp steps plus 16 spare bytes (a lane reads a little past its 4

@@ -280,7 +280,7 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
     slot = std::max(slot, d.tile_bytes);
     if (FMT == 1) {
       cls = std::max(cls, d.tile_bytes - d.cls_off);
-      thr = std::max(thr, ((d.ncls + 1) * Thr<K>::TS + 15) & ~15);
+      thr = std::max(thr, 32 + (((d.ncls + 1) * Thr<K>::TS + 15) & ~15));     // L_k, then the threshold rows
     }
   }
   const int n_ptab = (int) st->h_ptab.size();

@@ -109,7 +109,7 @@ def test_tile_layout_and_sizes():
     assert (ti[:, 0] == 1).all() and (ti[:, 1] >= 1).all() and (ti[:, 1] <= 254).all()
     for (k, _, r2, _, _), (_, ncls, tb) in zip(info, ti):
         padded = (int(r2) + 3 + 127) // 128 * 128
-        assert tb == 2 * (padded + 16) + 16 * ncls + (4 * ncls + 15) // 16 * 16
+        assert tb == 2 * (padded + 16) + 16 * ncls + (4 * (ncls + 1) + 15) // 16 * 16
     assert cplan.size()[2] == int(ti[:, 2].sum()) < tile_bytes
     p = mb.make_params(1000, 100, 9, 3)
     ns, nl, na = plan.output_sizes(p)
