@@ -51,6 +51,7 @@ extern "C" {
 /* ---- enums: pysplicing/pysplicing/__init__.py:2-13 ------------------- */
 #define MISOB200_START_AUTO      0
 #define MISOB200_START_UNIFORM   1
+#define MISOB200_START_RANDOM    2	/* Dirichlet(1) start, src/miso.c:388-404 */
 #define MISOB200_STOP_FIXEDNO    0
 #define MISOB200_ALGO_REASSIGN   0
 

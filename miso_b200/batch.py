@@ -40,10 +40,12 @@ class Gene:
 
 def make_params(n_iters=5000, burn_in=500, lag=10, n_chains=6, start=0, stop=0,
                 algo=0, device=0, seed=0):
-    if start not in (MISO_START_AUTO, MISO_START_UNIFORM):
+    if start not in (MISO_START_AUTO, MISO_START_UNIFORM, MISO_START_RANDOM):
+        # GIVEN: pysplicing.MISO passes start_psi=0 (pysplicing.c:99), unusable there too;
+        # LINEAR: NNLS deconvolution (solve.c:308-536), off the sampler path
         raise NotImplementedError(
-            "start=%r: only MISO_START_AUTO / MISO_START_UNIFORM run on the "
-            "device (misopy always passes AUTO, miso_sampler.py:210)" % (start,))
+            "start=%r: MISO_START_AUTO / UNIFORM / RANDOM run on the device "
+            "(misopy always passes AUTO, miso_sampler.py:210)" % (start,))
     if stop != MISO_STOP_FIXEDNO:
         raise NotImplementedError("stop=%r: only MISO_STOP_FIXEDNO" % (stop,))
     if algo != MISO_ALGO_REASSIGN:

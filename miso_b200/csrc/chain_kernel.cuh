@@ -181,6 +181,17 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   if (P.start == MISOB200_START_AUTO) {
     if (K == 2) { n_u = 1; alpha = 0.0; }     // one uniform drawn and discarded (miso.c:365)
     else alpha = 1.0 / (K - 1);
+  } else if (P.start == MISOB200_START_RANDOM) {
+    // psi ~ Dirichlet(1,...,1): K gamma(1,1) = -log(uniform) draws, normalised
+    // (splicing_rng_get_dirichlet, miso.c:309-326), alpha = logit(psi) (miso.c:202-217).
+    // sigma stays SIGMA: the reference leaves it unassigned on this branch.
+    const double g = 1.0 * -d_log(stream_uniform((unsigned long long) kk, gid, (uint32_t) chain, key));
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; i++) sum = sum + shfl_d(g, gb + i);
+    const double lpsi = d_log(d_div(g, sum));
+    alpha = lpsi - shfl_d(lpsi, gb + K - 1);
+    n_u = K;
   } else {
     alpha = 0.0;
   }
@@ -392,6 +403,7 @@ __global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? MISOB200_MINBLOCKS_CLA
     ClassRef cr;
     cr.ncls = FMT == 1 ? d.ncls : 0;
     cr.thr_s = smem_u32(slot + P.slot_bytes) + 32u;
+    cr.thrb_s = cr.thr_s + (uint32_t) Thr<K>::plane_a_bytes(cr.ncls);
     cr.l_s = smem_u32(slot + P.slot_bytes);
     cr.rec_s = smem_u32(slot) + (SMEM ? (uint32_t) d.cls_off : 0u);
     cr.meta_s = cr.rec_s + 16u * (uint32_t) cr.ncls;
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? MISOB200_MINBLOCKS_CLA
     } else if (FMT == 1) {
       // rows stay in global memory; the class records are small and go to the slot
       const uint4 *src = reinterpret_cast<const uint4 *>(P.tiles + d.tile_off + d.cls_off);
-      const int n16 = (int) (tile_bytes - (uint32_t) d.cls_off) >> 4;
+      const int n16 = (d.core_bytes - d.cls_off) >> 4;
       for (int i = lane; i < n16; i += 32) reinterpret_cast<uint4 *>(slot)[i] = __ldg(src + i);
     }
     if (FMT == 1 && lane < kMaxIso) reinterpret_cast<int *>(slot + P.slot_bytes)[lane] = d.L[lane];
@@ -413,7 +425,7 @@ __global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? MISOB200_MINBLOCKS_CLA
       uint32_t never[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) never[k] = 0u;        // rows hold ~t_k
-      Thr<K>::store(cr.thr_s + (uint32_t) (Thr<K>::TS * cr.ncls), never);
+      Thr<K>::store(cr.thr_s + (uint32_t) (Thr<K>::TSA * cr.ncls), cr.thrb_s + (uint32_t) (Thr<K>::TSB * cr.ncls), never);
     }
     if (SMEM) {
       mbar_wait(bar, phase);

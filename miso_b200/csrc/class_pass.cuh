@@ -33,31 +33,51 @@ namespace misob200 {
 
 constexpr double kThrMargin = 0x1p-15;
 
+// Philox blocks in flight per lane in the counting pass / the read-score pass
+#ifndef MISOB200_UNROLL_COUNT
+#define MISOB200_UNROLL_COUNT 2
+#endif
+#ifndef MISOB200_UNROLL_SCORE
+#define MISOB200_UNROLL_SCORE 1
+#endif
+constexpr int kUnrollCount = MISOB200_UNROLL_COUNT, kUnrollScore = MISOB200_UNROLL_SCORE;
+
+// Threshold rows live in two planes so that a row never spans more than 16 bytes: plane A
+// holds t_0..t_3 of every class (stride TSA <= 16), plane B t_4..t_6 (stride TSB, K >= 6).
+// A warp's LDS.128 is served a quarter-warp at a time; with one 32-byte row per class only
+// four of the eight 16-byte bank groups were ever addressed (2-way conflicts at best, ncu
+// showed the LSU pipe ~85 % busy at K = 8); with 16-byte rows class c sits in group c mod 8.
+// plan.cpp numbers the classes by falling read count, so the frequent ones get distinct groups.
 template <int K> struct Thr {
   static constexpr int NT = K - 1;                                          // thresholds per class
-  static constexpr int TS = NT <= 1 ? 4 : NT <= 2 ? 8 : NT <= 4 ? 16 : 32;   // bytes per class row
-  static __device__ __forceinline__ void load(uint32_t a, uint32_t (&t)[8]) {
+  static constexpr int TSA = NT <= 1 ? 4 : NT <= 2 ? 8 : 16;                // bytes per class, plane A
+  static constexpr int TSB = NT <= 4 ? 0 : NT == 5 ? 4 : NT == 6 ? 8 : 16;  // plane B
+  static __host__ __device__ constexpr int plane_a_bytes(int ncls) { return ((ncls + 1) * TSA + 15) & ~15; }
+  static __host__ __device__ constexpr int bytes(int ncls) { return plane_a_bytes(ncls) + (((ncls + 1) * TSB + 15) & ~15); }
+  static __device__ __forceinline__ void load(uint32_t a, uint32_t b, uint32_t (&t)[8]) {
     if (NT == 1) {
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t[0]) : "r"(a));
     } else if (NT == 2) {
       asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(t[0]), "=r"(t[1]) : "r"(a));
     } else {
       asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]) : "r"(a));
-      if (NT == 5) asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(t[4]) : "r"(a));
-      if (NT == 6) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+16];" : "=r"(t[4]), "=r"(t[5]) : "r"(a));
+      if (NT == 5) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t[4]) : "r"(b));
+      if (NT == 6) asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(t[4]), "=r"(t[5]) : "r"(b));
       if (NT == 7)
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]) : "r"(a));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]) : "r"(b));
     }
   }
-  static __device__ __forceinline__ void store(uint32_t a, const uint32_t (&t)[8]) {
+  static __device__ __forceinline__ void store(uint32_t a, uint32_t b, const uint32_t (&t)[8]) {
     if (NT == 1) {
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(t[0]) : "memory");
     } else if (NT == 2) {
       asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(t[0]), "r"(t[1]) : "memory");
     } else {
       asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]) : "memory");
-      if (NT > 4)
-        asm volatile("st.shared.v4.u32 [%0+16], {%1,%2,%3,%4};" ::"r"(a), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]) : "memory");
+      if (NT == 5) asm volatile("st.shared.u32 [%0], %1;" ::"r"(b), "r"(t[4]) : "memory");
+      if (NT == 6) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(b), "r"(t[4]), "r"(t[5]) : "memory");
+      if (NT == 7)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(b), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]) : "memory");
     }
   }
 };
@@ -77,7 +97,8 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
 struct ClassRef {
   uint32_t rec_s;    // ncls x 8 u16 ptab indices (0 = incompatible)
   uint32_t meta_s;   // (ncls + 1) x u32: bits 0-7 first compatible isoform, bit 8 uniform-code class
-  uint32_t thr_s;    // (ncls + 1) x Thr<K>::TS bytes of ~t_k, row ncls = null class (all 0: no test ever true)
+  uint32_t thr_s;    // plane A: (ncls + 1) x Thr<K>::TSA bytes of ~t_0..3, row ncls = null class (all 0: no test ever true)
+  uint32_t thrb_s;   // plane B: (ncls + 1) x Thr<K>::TSB bytes of ~t_4..6
   uint32_t l_s;      // 8 ints: L_k of the paired-end read score, lp = L_k - (code - 1) (miso_paired.c:409-410)
   int ncls;
 };
@@ -119,7 +140,7 @@ __device__ __forceinline__ bool thr_update(const ClassRef &cr, uint32_t ptab_s, 
         bad = bad || !good;
       }
     }
-    Thr<K>::store(cr.thr_s + (uint32_t) (Thr<K>::TS * c), t);
+    Thr<K>::store(cr.thr_s + (uint32_t) (Thr<K>::TSA * c), cr.thrb_s + (uint32_t) (Thr<K>::TSB * c), t);
   }
   bad = __any_sync(0xffffffffu, bad);
   __syncwarp();
@@ -150,7 +171,7 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
                                                 const double *__restrict__ neglog, int n_neglog,
                                                 int (&cnt)[K], double &rp) {
   using TM = TileMem<SMEM>;
-  constexpr int NT = Thr<K>::NT, TS = Thr<K>::TS;
+  constexpr int NT = Thr<K>::NT, TSA = Thr<K>::TSA, TSB = Thr<K>::TSB;
   const int lane = threadIdx.x & 31;
   const int o = (int) (n_u & 3ull);
   const uint32_t Q0 = (uint32_t) (n_u >> 2);
@@ -164,11 +185,11 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
   const int hs = 3 - o;                               // 16-bit codes: halfwords into the 8-halfword window
   const bool hb = (hs >> 1) != 0;
   const uint32_t hsh = 16u * (uint32_t) (hs & 1);
-  const uint32_t thr_s = cr.thr_s;
+  const uint32_t thr_s = cr.thr_s, thrb_s = cr.thrb_s;
   const uint32_t ncls = (uint32_t) cr.ncls;
   double rp_lane = 0.0;
   uint32_t tot = 0;                                   // MODE 1: sum of the G_k so far
-#pragma unroll (MODE == 0 ? 2 : 1)
+#pragma unroll (MODE == 0 ? kUnrollCount : kUnrollScore)
   for (int s = 0; s < nsteps; s++) {
     uint32_t x[4];
     philox4x32_10(Q0 + (uint32_t) (lane + 32 * s), 0u, gene, chain, key, x);
@@ -190,7 +211,7 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
     for (int i = 0; i < 4; i++) {
       const uint32_t id = __byte_perm(ids, 0u, 0x4440u | (uint32_t) i);
       uint32_t nt[8];
-      Thr<K>::load(thr_s + id * (uint32_t) TS, nt);
+      Thr<K>::load(thr_s + id * (uint32_t) TSA, thrb_s + id * (uint32_t) TSB, nt);
 #pragma unroll
       for (int k = 0; k < NT; k++)      // G_k += (w > t_k): carry out of w + ~t_k, added with carry
         asm("{\n\t.reg .u32 j;\n\tadd.cc.u32 j, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(G[k]) : "r"(x[i]), "r"(nt[k]));

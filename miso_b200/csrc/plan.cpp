@@ -15,6 +15,7 @@
 //     src/qsort.c through include/matrix.pmt:579-589).
 #include "plan.hpp"
 
+#include <algorithm>
 #include <array>
 #include <atomic>
 #include <cmath>
@@ -377,21 +378,39 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
     }
   }
 
+  if (class_ok) {
+    // number the classes by falling read count: class c's threshold row lives in the 16-byte
+    // bank group c mod 8 of shared memory (class_pass.cuh), so the classes most lanes ask for
+    // in the same LDS should sit in different groups
+    const int n = (int) cls_keys.size();
+    std::vector<int> by(n), to(n);
+    for (int c = 0; c < n; c++) by[c] = c;
+    std::stable_sort(by.begin(), by.end(), [&](int a, int b) { return cls_size[a] > cls_size[b]; });
+    std::vector<std::array<uint16_t, kMaxIso>> keys2(n);
+    std::vector<int> size2(n);
+    for (int c = 0; c < n; c++) { to[by[c]] = c; keys2[c] = cls_keys[by[c]]; size2[c] = cls_size[by[c]]; }
+    cls_keys.swap(keys2);
+    cls_size.swap(size2);
+    for (int i = 0; i < R2; i++) cls_id[i] = (uint8_t) to[cls_id[i]];
+  }
+
   const int cb = plan.wide ? 2 : 1;
   const int padded = round_up(R2 + kTilePadFront, 128);
   if (class_ok) {
-    // class tile: id row (bytes; the padding carries the null class id ncls), uniform-code
-    // row (bytes, or 16-bit when the insert model has more than 255 fragment lengths),
-    // class records: ncls x 8 ptab indices (u16), then ncls meta words
-    // (bits 0-7 first compatible isoform, bit 8 uniform-code class), one more for the null class.
+    // class tile: id row (bytes; the padding carries the null class id ncls), class records:
+    // ncls x 8 ptab indices (u16), then ncls meta words (bits 0-7 first compatible isoform,
+    // bit 8 uniform-code class), one more for the null class -- these two are the "core" every
+    // pass reads -- then the uniform-code row (bytes, or 16-bit when the insert model has more
+    // than 255 fragment lengths).
     const int ncls = (int) cls_keys.size();
     d.format = 1;
     d.ncls = ncls;
     d.row_bytes = padded + 16;
-    d.ucode_off = d.row_bytes;
-    d.cls_off = d.ucode_off + padded * cb + 16;
+    d.cls_off = d.row_bytes;
+    d.core_bytes = d.cls_off + ncls * 16 + round_up((ncls + 1) * 4, 16);
+    d.ucode_off = d.core_bytes;      // last: only the read-score passes and the literal rule read it
     d.flag_off = 0;
-    d.tile_bytes = d.cls_off + ncls * 16 + round_up((ncls + 1) * 4, 16);
+    d.tile_bytes = d.ucode_off + padded * cb + 16;
     out.tile.assign((size_t) d.tile_bytes, 0);
     std::memset(out.tile.data(), ncls, (size_t) d.row_bytes);
     uint8_t *uc = out.tile.data() + d.ucode_off;

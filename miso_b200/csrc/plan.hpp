@@ -42,12 +42,13 @@ struct GeneDesc {
   int status;
   int flag_off;                  // byte offset of the flag row (always u8) inside the tile
   int tile_bytes;                // whole tile, multiple of 16
-  int pad_[2];
+  int core_bytes;                // class format: id row + class records (what quad_kernel.cuh keeps in shared memory)
+  int pad_[1];
   // ---- class format (format == 1, class_kernel.cuh) -------------------------
   int format;                    // 0: dense code rows + flag row; 1: class ids + uniform codes + class records
   int ncls;                      // weight classes among the drawing reads (<= kMaxClasses)
+  int cls_off;                   // byte offset of the class records (ncls x 8 u16 ptab indices, then ncls + 1 u32 meta)
   int ucode_off;                 // byte offset of the uniform-code row (u8, or u16 when the plan is "wide")
-  int cls_off;                   // byte offset of the class records (ncls x 8 u16 ptab indices, then ncls u32 meta)
   int g_always[kMaxIso];         // drawing reads whose first compatible isoform comes after k (their test k
                                  // is true whatever the uniform: the cumulative sum is still an exact 0)
 };

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -15,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "chain_kernel.cuh"
+#include "quad_kernel.cuh"
 #include "plan.hpp"
 
 namespace misob200 {
@@ -71,8 +73,9 @@ static int check_params(const misob200_params_t &p) {
     set_error("invalid sampler parameters (iterations/burn-in/lag/chains)");
     return MISOB200_EINVAL;
   }
-  if (p.start != MISOB200_START_AUTO && p.start != MISOB200_START_UNIFORM) {
-    set_error("only MISO_START_AUTO and MISO_START_UNIFORM are implemented");
+  if (p.start != MISOB200_START_AUTO && p.start != MISOB200_START_UNIFORM && p.start != MISOB200_START_RANDOM) {
+    set_error("only MISO_START_AUTO, MISO_START_UNIFORM and MISO_START_RANDOM are implemented "
+              "(GIVEN has no start_psi at the pysplicing boundary, LINEAR needs the NNLS solver)");
     return MISOB200_UNIMPLEMENTED;
   }
   if (p.stop != MISOB200_STOP_FIXEDNO) {
@@ -279,8 +282,8 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
     const GeneDesc &d = plan.desc[g];
     slot = std::max(slot, d.tile_bytes);
     if (FMT == 1) {
-      cls = std::max(cls, d.tile_bytes - d.cls_off);
-      thr = std::max(thr, 32 + (((d.ncls + 1) * Thr<K>::TS + 15) & ~15));     // L_k, then the threshold rows
+      cls = std::max(cls, d.core_bytes - d.cls_off);
+      thr = std::max(thr, 32 + Thr<K>::bytes(d.ncls));     // L_k, then the two planes of threshold rows
     }
   }
   const int n_ptab = (int) st->h_ptab.size();
@@ -296,6 +299,12 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   auto kern = plan.wide ? (in_smem ? chain_kernel<K, WARPS, true, true, FMT> : chain_kernel<K, WARPS, false, true, FMT>)
                         : (in_smem ? chain_kernel<K, WARPS, true, false, FMT> : chain_kernel<K, WARPS, false, false, FMT>);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  {
+    // the seven K buckets run as concurrent kernels: give them all the same L1/shared split
+    const char *cv = std::getenv("MISOB200_CARVEOUT");
+    const int carve = cv ? std::atoi(cv) : -2;
+    if (carve >= -1) CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  }
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
   if (per_sm < 1) { set_error("chain kernel does not fit on an SM"); return MISOB200_ECUDA; }
@@ -331,6 +340,88 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   return 0;
 }
 
+// Four gene-chains per warp (quad_kernel.cuh): class-format buckets whose core tiles fit.
+// Returns 1 when it launched, 0 when the caller should use chain_kernel instead.
+template <int K>
+static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
+  const int b = (kMaxIso + 1) + K;
+  const auto &v = st->items[b];
+  constexpr int WARPS = 4;
+  int core = 0, thr = 0;
+  for (int g : v) {
+    const GeneDesc &d = plan.desc[g];
+    core = std::max(core, d.core_bytes);
+    thr = std::max(thr, 32 + Thr<K>::bytes(d.ncls));
+  }
+  // The quad layout pays when the per-iteration scalar part dominates, i.e. for genes with few
+  // reads that draw; with many reads the counting pass dominates and costs the same either
+  // way, while four tiles per warp lower the occupancy (measured, profiles/README.md).
+  {
+    long long r2 = 0;
+    for (int g : v) r2 += plan.desc[g].R2;
+    const char *lim = std::getenv("MISOB200_QUAD_MAX_READS");
+    const char *cpw = std::getenv("MISOB200_CHAINS_PER_WARP");      // "4": tests force the layout
+    const long long max_mean = lim ? std::atoll(lim) : (cpw && std::atoi(cpw) == 4) ? (1LL << 40) : 1600;
+    if (!v.empty() && r2 > max_mean * (long long) v.size()) return 0;
+  }
+  const int slot = ((core + 127) & ~127) + 32;     // 32 mod 128: the four groups' id words fall in different banks
+  const size_t smem = (size_t) WARPS * (16 + (size_t) kQuad * (slot + thr));
+  if (smem > 227 * 1024) return 0;
+  auto kern = plan.wide ? quad_kernel<K, WARPS, true> : quad_kernel<K, WARPS, false>;
+  *rc = MISOB200_ECUDA;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
+    set_error(std::string("quad kernel: ") + cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
+  if (per_sm < 1) { cudaGetLastError(); *rc = 0; return 0; }
+  const long long n_items = (long long) v.size() * st->params.n_chains;
+  long long blocks = (n_items + WARPS * kQuad - 1) / (WARPS * kQuad);
+  blocks = std::min<long long>(blocks, (long long) per_sm * st->sm_count);
+
+  ChainParams P;
+  P.desc = st->d_desc;
+  P.items = st->d_items + st->item_off[b];
+  P.n_genes = (int) v.size();
+  P.n_chains = st->params.n_chains;
+  P.tiles = st->d_tiles;
+  P.ptab = st->d_ptab;
+  P.n_ptab = (int) st->h_ptab.size();
+  P.ptab_min = 1.0;
+  for (double v : plan.ptab) if (v > 0 && v < P.ptab_min) P.ptab_min = v;
+  P.samples = st->d_samples;
+  P.loglik = st->d_loglik;
+  P.drawn = st->d_drawn;
+  P.accrej = st->d_accrej;
+  P.queue = st->d_queue + b;
+  P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
+  P.start = st->params.start;
+  P.key = philox_expand_key(st->params.seed);
+  P.slot_bytes = slot;
+  P.neglog = st->d_neglog;
+  P.n_neglog = st->n_neglog;
+  P.thr_bytes = thr;
+  kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[b]>>>(P);
+  if (cudaGetLastError() != cudaSuccess) { set_error("quad kernel launch failed"); return 1; }
+  (*launches)++;
+  *rc = 0;
+  return 1;
+}
+
+static int launch_quad_k(Plan &plan, DevState *st, int k, int *nl, int *rc) {
+  switch (k) {
+    case 2: return launch_quad<2>(plan, st, nl, rc);
+    case 3: return launch_quad<3>(plan, st, nl, rc);
+    case 4: return launch_quad<4>(plan, st, nl, rc);
+    case 5: return launch_quad<5>(plan, st, nl, rc);
+    case 6: return launch_quad<6>(plan, st, nl, rc);
+    case 7: return launch_quad<7>(plan, st, nl, rc);
+    case 8: return launch_quad<8>(plan, st, nl, rc);
+  }
+  return 0;
+}
+
 template <int FMT>
 static int launch_k(Plan &plan, DevState *st, int k, int *nl) {
   switch (k) {
@@ -357,14 +448,35 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
   CK(cudaMemsetAsync(st->d_loglik, 0, std::max<long long>(st->n_loglik, 1) * sizeof(double), st->stream));
   CK(cudaEventRecord(st->ev[2], st->stream));
   int rc = 0;
+  // development only (tools/ab_bench.py): time one isoform-count bucket by itself; the
+  // other genes' outputs are then left unset
+  const char *only = std::getenv("MISOB200_ONLY_K");
+  const int only_k = only ? std::atoi(only) : 0;
+  const bool serial = std::getenv("MISOB200_SERIAL") != nullptr;
+  // chains per warp: four (quad_kernel.cuh) once there are enough gene-chains to fill the
+  // machine that way, else one (chain_kernel.cuh: a chain alone on a warp finishes sooner).
+  // MISOB200_CHAINS_PER_WARP = 1 | 4 overrides (tests run both).
+  bool quad;
+  {
+    long long n_class_items = 0;
+    for (int k = 2; k <= kMaxIso; k++) n_class_items += (long long) st->items[(kMaxIso + 1) + k].size() * st->params.n_chains;
+    quad = n_class_items >= 2LL * st->sm_count * 16;
+    const char *cpw = std::getenv("MISOB200_CHAINS_PER_WARP");
+    if (cpw) quad = std::atoi(cpw) == 4;
+  }
+  int prev = -1;
   // dense buckets first (slowest per read), big K before small K (longest chains)
   for (int fmt = 0; fmt < 2 && !rc; fmt++)
     for (int k = kMaxIso; k >= 2 && !rc; k--) {
       const int b = fmt * (kMaxIso + 1) + k;
       if (st->items[b].empty()) continue;
+      if (only_k && k != only_k) continue;
       CK(cudaStreamWaitEvent(st->kstream[b], st->ev[2], 0));
+      if (serial && prev >= 0) CK(cudaStreamWaitEvent(st->kstream[b], st->kdone[prev], 0));
+      prev = b;
       CK(cudaEventRecord(st->kbeg[b], st->kstream[b]));
-      rc = fmt ? launch_k<1>(plan, st, k, &nl) : launch_k<0>(plan, st, k, &nl);
+      if (!(fmt && quad && launch_quad_k(plan, st, k, &nl, &rc)))
+        rc = fmt ? launch_k<1>(plan, st, k, &nl) : launch_k<0>(plan, st, k, &nl);
       if (rc) return rc;
       CK(cudaEventRecord(st->kend[b], st->kstream[b]));
       CK(cudaEventRecord(st->kdone[b], st->kstream[b]));

@@ -18,6 +18,10 @@
  *                 a = (x0 << 21) | (x1 >> 11)     53 bits
  *                 b = (x2 << 21) | (x3 >> 11)     53 bits
  *                 z = sqrt(-2 ln((a + 1) 2^-53)) * cos(2 pi * b 2^-53)
+ *   gamma(a=1, scale) : scale * -ln(next uniform)   (an Exp(1) draw by inversion)
+ *                 -- the only shape the path asks for: the START_RANDOM
+ *                 Dirichlet draw, src/miso.c:309-326 called with alpha = 1 at
+ *                 :388-404; consumes one uniform of the tag-0 sequence.
  * The n-th call of get_real / get_norm inside one splicing_miso[_paired]
  * invocation returns uniform n / normal n (SURVEY.md appendix C gives the
  * order in which the reference consumes them).
@@ -84,6 +88,10 @@ static inline double phx_next_uniform(phx_stream_t *s) {
 }
 static inline double phx_next_normal(phx_stream_t *s) {
   return phx_normal_at(s, s->n_norm++);
+}
+/* gamma(1, scale); other shapes are never requested on the sampler path */
+static inline double phx_next_gamma1(phx_stream_t *s, double scale) {
+  return scale * -log(phx_next_uniform(s));
 }
 
 #endif

@@ -41,6 +41,16 @@ static double refh_get_norm(void *state) {
   return phx_next_normal((phx_stream_t *) state);
 }
 
+/* gamma(1, scale) only: the START_RANDOM Dirichlet draw (src/miso.c:318 with
+   alpha = 1, :394).  Any other shape is not part of the stream definition. */
+static double refh_get_gamma(void *state, double a, double scale) {
+  if (a != 1.0) {
+    fprintf(stderr, "ref_harness: gamma shape %g is not defined by the stream\n", a);
+    abort();
+  }
+  return phx_next_gamma1((phx_stream_t *) state, scale);
+}
+
 static splicing_rng_type_t refh_rngtype = {
   /* name= */      "miso-b200 stream v1 (Philox4x32-10)",
   /* min= */       0,
@@ -53,7 +63,7 @@ static splicing_rng_type_t refh_rngtype = {
   /* get_norm= */  refh_get_norm,
   /* get_geom= */  0,
   /* get_binom= */ 0,
-  /* get_gamma= */ 0
+  /* get_gamma= */ refh_get_gamma
 };
 
 static splicing_rng_t refh_saved_default;
@@ -84,6 +94,20 @@ static void refh_install_rng(int rng_mode, uint64_t seed, uint32_t gene,
 
 void refh_rng_counts(uint64_t *n_unif, uint64_t *n_norm) {
   *n_unif = refh_stream.n_unif; *n_norm = refh_stream.n_norm;
+}
+
+/* START_RANDOM leaves `sigma' of splicing_miso[_paired] unassigned
+   (src/miso.c:655 vs :388-404; src/miso_paired.c:264): the unmodified
+   reference then reads whatever its stack slot holds.  To compare it with the
+   port on that branch the harness fills the stack region the callee's frame
+   is about to occupy with the bit pattern of SIGMA = 0.2/K/K right before the
+   call.  This relies on the compiler giving the address-taken local its own
+   slot and is checked, not assumed: tests/test_oracle_vs_reference.py only
+   accepts the comparison when the outputs agree bit for bit.            */
+static void __attribute__((noinline)) refh_paint_stack(double v) {
+  volatile double pad[4096];
+  int i;
+  for (i = 0; i < 4096; i++) { pad[i] = v; }
 }
 
 /* splicing_miso prints "no chains: N" on every call (src/miso.c:837).  Keep
@@ -319,6 +343,7 @@ int refh_miso_se(int nexons, const int *exons, int isolen,
 
   refh_install_rng(rng_mode, seed, gene_id, chain_id);
   refh_quiet_begin();
+  if (start == 2) { refh_paint_stack(0.2 / (double) noiso / (double) noiso); }
   ret = splicing_miso(&gff, 0, &position, cigars, readLength, overhang,
 		      noChains, noIterations, /*maxIterations=*/ 100000,
 		      noBurnIn, noLag, &hyp, SPLICING_ALGO_REASSIGN,
@@ -386,6 +411,7 @@ int refh_miso_pe(int nexons, const int *exons, int isolen,
   memset(&rd, 0, sizeof(rd));
 
   refh_install_rng(rng_mode, seed, gene_id, chain_id);
+  if (start == 2) { refh_paint_stack(0.2 / (double) noiso / (double) noiso); }
   ret = splicing_miso_paired(&gff, 0, &position, cigars, readLength,
 			     overhang, noChains, noIterations,
 			     /*maxIterations=*/ 100000, noBurnIn, noLag,

@@ -31,8 +31,15 @@ def check(case, samples, loglik, assignment, acc, rej):
         assert abs(a.mean() - b.mean()) < 1e-3 and abs(a[lo] - b[lo]) < 1e-3 and abs(a[hi] - b[hi]) < 1e-3
 
 
+@pytest.fixture(params=[4, 1], ids=["quad", "single"])
+def chains_per_warp(request, monkeypatch):
+    """four gene-chains per warp (quad_kernel.cuh, what big batches run) / one (chain_kernel.cuh)"""
+    monkeypatch.setenv("MISOB200_CHAINS_PER_WARP", str(request.param))
+    return request.param
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
-def test_pysplicing_entry_points_match_reference_golden(mb, case):
+def test_pysplicing_entry_points_match_reference_golden(mb, case, chains_per_warp):
     import pysplicing
     gene = pysplicing.createGene(case.exons, case.isoforms)
     pos, cig = tuple(int(p) for p in case.pos), tuple(case.cig)

@@ -17,12 +17,26 @@ def mb():
     return miso_b200
 
 
-# tile_format -1: class tiles (integer thresholds per weight class, class_pass.cuh);
-# 0: dense tiles (per-read fp64 weights, dense_pass.cuh).  Both must reproduce the oracle.
-FORMATS = [-1, 0]
+# Every device layout must reproduce the oracle:
+#   "quad"   class tiles (integer thresholds per weight class, class_pass.cuh), four gene-chains
+#            per warp (quad_kernel.cuh) -- what a full-size batch runs
+#   "single" class tiles, one gene-chain per warp (chain_kernel.cuh) -- small batches
+#   "dense"  dense tiles (per-read fp64 weights, dense_pass.cuh) -- genes with too many classes
+LAYOUTS = ["quad", "single", "dense"]
 
 
-@pytest.mark.parametrize("tile_format", FORMATS)
+@pytest.fixture(params=[4, 1], ids=["quad", "single"])
+def chains_per_warp(request, monkeypatch):
+    monkeypatch.setenv("MISOB200_CHAINS_PER_WARP", str(request.param))
+    return request.param
+
+
+@pytest.fixture(params=LAYOUTS)
+def tile_format(request, monkeypatch):
+    monkeypatch.setenv("MISOB200_CHAINS_PER_WARP", "4" if request.param == "quad" else "1")
+    return 0 if request.param == "dense" else -1
+
+
 @pytest.mark.parametrize("kind,n_genes,reads", [(0, 24, 300), (1, 32, 400)])
 def test_chain_matches_oracle(mb, port, kind, n_genes, reads, tile_format):
     w = mb.Workload(kind, n_genes, reads, 36, 250.0, 900.0, 4.0, seed=11, first_gene_id=100)
@@ -58,7 +72,6 @@ def test_summary_matches_numpy(mb):
         assert s["accepted"] == r["rundata"][5] and s["rejected"] == r["rundata"][6]
 
 
-@pytest.mark.parametrize("tile_format", FORMATS)
 def test_wide_insert_model_uses_16_bit_codes(mb, port, tile_format):
     """sd = 50 -> 401 fragment lengths: codes no longer fit a byte; the 16-bit tile variant
     of the kernel must make the same decisions."""
@@ -98,7 +111,7 @@ def _cassette_batch(mb, n_genes, n_pairs, exon_len, two_cassettes, seed):
 
 
 @pytest.mark.parametrize("two_cassettes,want_format", [(False, 1), (True, 0)])
-def test_reads_with_two_fragment_lengths(mb, port, two_cassettes, want_format):
+def test_reads_with_two_fragment_lengths(mb, port, two_cassettes, want_format, chains_per_warp):
     """Non-uniform weight classes.  One short cassette exon: up to ~200 classes, still a class
     tile.  Two: more than 254 classes, the plan must fall back to the dense tile by itself."""
     rb, raw = _cassette_batch(mb, 10, 1500 if two_cassettes else 700, 61, two_cassettes, seed=5)
@@ -112,3 +125,17 @@ def test_reads_with_two_fragment_lengths(mb, port, two_cassettes, want_format):
     for g, wl_gene in enumerate(raw):
         want = oracle_gene(port, wl_gene, True, params, gene_id=g)
         assert_gene_parity(plan.gene_result(out, g), want, tag="cassette gene %d" % g)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_start_random_and_uniform(mb, port, kind, chains_per_warp):
+    """MISO_START_RANDOM: Dirichlet(1) start from K gamma(1,1) = -log(uniform) draws
+    (src/miso.c:388-404, :309-326) and MISO_START_UNIFORM (:372-386)."""
+    w = mb.Workload(kind, 16, 300, 36, 250.0, 900.0, 4.0, seed=17, first_gene_id=40)
+    plan = mb.Plan().append(w)
+    for start in (mb.MISO_START_RANDOM, mb.MISO_START_UNIFORM):
+        params = mb.make_params(n_iters=400, burn_in=100, lag=5, n_chains=2, start=start, seed=9)
+        out = plan.run(params)
+        for g in range(16):
+            want = oracle_gene(port, w.gene(g), kind == 1, params, gene_id=40 + g)
+            assert_gene_parity(plan.gene_result(out, g), want, tag="start %d kind %d gene %d" % (start, kind, g))

@@ -40,10 +40,12 @@ def test_rerun_is_bit_reproducible_and_seed_matters(mb):
     assert not np.array_equal(a["samples"], c["samples"])
 
 
-def test_cfg2_and_cfg3_sized_batches_have_sane_posteriors(mb):
+@pytest.mark.parametrize("chains_per_warp", [4, 1])
+def test_cfg2_and_cfg3_sized_batches_have_sane_posteriors(mb, monkeypatch, chains_per_warp):
     """Size-independent properties on thousands of genes: psi on the simplex,
     every compatible read assigned to a compatible isoform, counts add up,
     accept + reject = iterations * chains, posterior mean near the simulated truth."""
+    monkeypatch.setenv("MISOB200_CHAINS_PER_WARP", str(chains_per_warp))
     for kind, G, R in ((0, 3000, 1000), (1, 3000, 2000)):
         w = mb.Workload(kind, G, R, 36, 250.0, 900.0, 4.0, seed=31)
         plan = mb.Plan(keep_match=False).append(w)

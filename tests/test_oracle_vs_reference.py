@@ -57,3 +57,31 @@ def test_port_equals_reference(ref, port, t):
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     for k in ra:
         np.testing.assert_array_equal(ra[k], rb[k], err_msg=k)   # NaN-free by construction here
+
+
+@pytest.mark.parametrize("t", range(6))
+def test_start_random_port_equals_reference(ref, port, t):
+    """MISO_START_RANDOM (Dirichlet start via gamma draws, src/miso.c:388-404, :309-326).
+    The reference reads `sigma` uninitialised on this branch; the harness pre-loads that
+    stack slot with SIGMA (oracle/ref_harness.c refh_paint_stack) -- agreement bit for bit
+    with the port, which sets sigma = SIGMA, shows the pre-load took."""
+    rng = np.random.default_rng(7000 + t)
+    K = int(rng.integers(2, 9))
+    ex, iso = _gene(rng, K, 0)
+    psi = rng.dirichlet(np.ones(K))
+    R, rl, C = int(rng.integers(20, 300)), 36, int(rng.integers(1, 4))
+    kw = dict(overhang=1, chains=C, seed=t, gene_id=t, start=2)
+    if t % 2 == 0:
+        pos, cig, _ = ref.simulate_se(ex, iso, psi, R, rl, seed=t)
+        ra, rb = ref.miso_se(ex, iso, pos, cig, rl, 300, 50, 5, **kw), port.miso_se(ex, iso, pos, cig, rl, 300, 50, 5, **kw)
+    else:
+        pos, cig, _ = ref.simulate_pe(ex, iso, psi, R, rl, 250.0, 900.0, 4.0, seed=t)
+        ra = ref.miso_pe(ex, iso, pos, cig, rl, 250.0, 900.0, 4.0, 300, 50, 5, **kw)
+        rb = port.miso_pe(ex, iso, pos, cig, rl, 250.0, 900.0, 4.0, 300, 50, 5, **kw)
+    for k in ra:
+        np.testing.assert_array_equal(ra[k], rb[k], err_msg=k)
+    # and the start differs from AUTO's (the branch really ran)
+    kw["start"] = 0
+    rc = (port.miso_se(ex, iso, pos, cig, rl, 300, 50, 5, **kw) if t % 2 == 0 else
+          port.miso_pe(ex, iso, pos, cig, rl, 250.0, 900.0, 4.0, 300, 50, 5, **kw))
+    assert not np.array_equal(rb["samples"], rc["samples"])
