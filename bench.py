@@ -219,7 +219,26 @@ def build_plan(mb, wl, n_genes, first_gene_id, chunk=5000):
     return plan, t_gen, t_plan
 
 
+_JSON_OUT = None
+
+
+def keep_stdout_for_json():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints
+    its version banner on fd 1): keep the real stdout aside for the JSON line and point fd 1
+    at stderr for everything else."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    keep_stdout_for_json()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -264,7 +283,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": base["cores"], "kind": base["kind"],
                                  "sample": base["sample"]},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ GPU arm
@@ -379,7 +398,7 @@ def main():
             "setup_seconds": {"synthetic_generation": t_gen, "host_plan_stage": t_plan},
             "wall_ms_per_resident_step": 1e3 * wall_res / args.steps,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         lib.misob200_comm_destroy()
     return 0
