@@ -35,6 +35,73 @@
 
 namespace misob200 {
 
+// A gene-chain is 5000 dependent iterations -- tens of milliseconds on one warp -- and the
+// chains of a K bucket all cost about the same, so handing out whole chains makes the
+// bucket run in lock-stepped waves with a nearly empty last one (bench: 3.02 waves at
+// K = 8 took the time of ~3.6).  Chains are therefore cut into SEGMENTS of seg_len steps and
+// handed from warp to warp through a ready queue per bucket: a warp that finishes a segment
+// stores the chain's ChainState, appends the work unit (one chain here, four consecutive
+// chains in quad_kernel.cuh) to the ring and takes the oldest ready unit.  Pop number p is
+// unit p itself for p < n_units (first segments), else the (p - n_units)-th push; it can only
+// wait when nothing at all is ready, and then some running warp is about to push.
+// Everything else a chain carries across iterations is a deterministic function of the
+// record: the current point's psi, log psi ... are re-derived from alpha, thresholds
+// recomputed, normals are indexed by the iteration number -- the results do not depend on
+// seg_len (tests/test_gpu_parity.py::test_results_do_not_depend_on_segment_length).
+struct ChainState {
+  double alpha[kMaxIso - 1];
+  double rp_drawn;
+  unsigned long long n_u;    // uniforms consumed
+  int cnt[kMaxIso];          // reads assigned per isoform (drawn + fixed)
+  int lagc, n_rec, acc, rej;
+  int have_rp, pad_;
+};
+static_assert(sizeof(ChainState) % 16 == 0, "ChainState is 16-byte aligned");
+
+constexpr unsigned kRingEmpty = 0xffffffffu;
+#ifndef MISOB200_POLL_NS
+#define MISOB200_POLL_NS 500
+#endif
+
+// Pop: returns the unit of pop number p (lane 0 polls; relaxed loads served by L2 so that the
+// SM's L1 is not invalidated on every poll, one acquire fence at the end).
+#ifdef MISOB200_SEG_DEBUG
+__device__ unsigned long long g_seg_dbg[8];    // polls, wait cycles, pops, ring pops
+#endif
+__device__ __forceinline__ unsigned ring_pop(const unsigned *ring, unsigned p, unsigned n_units) {
+#ifdef MISOB200_SEG_DEBUG
+  atomicAdd(&g_seg_dbg[2], 1ull);
+#endif
+  if (p < n_units) return p;
+  const unsigned *slot = ring + (p - n_units);
+  unsigned v;
+#ifdef MISOB200_SEG_DEBUG
+  const long long t0 = clock64();
+  unsigned long long polls = 0;
+#endif
+  while (true) {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+    if (v != kRingEmpty) break;
+    __nanosleep(MISOB200_POLL_NS);
+#ifdef MISOB200_SEG_DEBUG
+    polls++;
+#endif
+  }
+#ifdef MISOB200_SEG_DEBUG
+  atomicAdd(&g_seg_dbg[0], polls);
+  atomicAdd(&g_seg_dbg[1], (unsigned long long) (clock64() - t0));
+  atomicAdd(&g_seg_dbg[3], 1ull);
+#endif
+  __threadfence();
+  return v;
+}
+// Push: the caller's ChainState stores are ordered before the slot by the fence.
+__device__ __forceinline__ void ring_push(unsigned *ring, unsigned *tail, unsigned unit) {
+  __threadfence();
+  const unsigned q = atomicAdd(tail, 1u);
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ring + q), "r"(unit) : "memory");
+}
+
 struct ChainParams {
   const GeneDesc *desc;
   const int *items;          // gene indices of this K bucket, longest first
@@ -56,6 +123,13 @@ struct ChainParams {
   const double *neglog;      // neglog[n] = -log(n), n < n_neglog (read scores, miso_paired.c:409-411)
   int n_neglog;
   int thr_bytes;             // shared-memory bytes per warp for the threshold rows (after the slot)
+  // chain segments (see ChainState)
+  int seg_len;               // steps per segment (a step is the start-up, m = -1, or an iteration)
+  int n_seg;                 // ceil((n_iters + 1) / seg_len)
+  ChainState *state;         // [gene][chain]
+  int *progress;             // [gene][chain]: segments completed (touched by the chain's current holder only)
+  unsigned *ring;            // this bucket's ready queue: n_units * (n_seg - 1) slots, all kRingEmpty at launch
+  unsigned *ring_tail;       // pushes so far
 };
 
 }  // namespace misob200
@@ -154,7 +228,8 @@ __device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb) {
 
 template <int K, bool SMEM, bool WIDE, int FMT>
 __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_index, int chain,
-                          typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s, const ClassRef &cr) {
+                          typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s, const ClassRef &cr,
+                          int m_begin, int m_end) {
   constexpr int len = K - 1;
   const int lane = threadIdx.x & 31;
   const int gb = lane & 24, mi = lane & 7, grp = lane >> 3;
@@ -175,10 +250,15 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   const PhiloxKey &key = P.key;
   const int *L = d.L;
 
+  ChainState *const st = P.state + ((long long) gene_index * P.n_chains + chain);
+  const bool fresh = m_begin < 0;
   unsigned long long n_u = 0;
   // ---- start state, splicing_drift_proposal_init (miso.c:330-447) ----------
   double alpha;            // replicated in every group: member i < K-1 holds alpha_i
-  if (P.start == MISOB200_START_AUTO) {
+  if (!fresh) {
+    alpha = st->alpha[mi < len ? mi : 0];
+    n_u = st->n_u;
+  } else if (P.start == MISOB200_START_AUTO) {
     if (K == 2) { n_u = 1; alpha = 0.0; }     // one uniform drawn and discarded (miso.c:365)
     else alpha = 1.0 / (K - 1);
   } else if (P.start == MISOB200_START_RANDOM) {
@@ -199,9 +279,9 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   // normals are produced 32 at a time into a 64-entry window (lane l holds normals
   // zbase + l and zbase + 32 + l); iteration m consumes normals (m+1)*len .. +len-1
   // (miso.c:851 -> :192-196), a batch looks kSpec iterations ahead
-  uint32_t zbase = 0u;
-  double zbuf0 = stream_normal((uint32_t) lane, gid, (uint32_t) chain, key);
-  double zbuf1 = stream_normal(32u + (uint32_t) lane, gid, (uint32_t) chain, key);
+  uint32_t zbase = ((uint32_t) (m_begin + 1) * (uint32_t) len) & ~31u;
+  double zbuf0 = stream_normal(zbase + (uint32_t) lane, gid, (uint32_t) chain, key);
+  double zbuf1 = stream_normal(zbase + 32u + (uint32_t) lane, gid, (uint32_t) chain, key);
 
   Derived cur;             // replicated in every group
   cur.psi = cur.lp = cur.q = cur.dir = cur.prod = 0.0;
@@ -210,6 +290,14 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   int cnt_k = 0;           // member k: reads currently assigned to isoform k (every group)
   double rp_drawn = 0.0;
   int lagc = 0, n_rec = 0, acc = 0, rej = 0;
+  bool have_rp = false;
+  if (!fresh) {            // resume: the current point is a function of alpha
+    cur = derive<K>(alpha, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
+    cnt_k = st->cnt[kk];
+    rp_drawn = st->rp_drawn;
+    lagc = st->lagc; n_rec = st->n_rec; acc = st->acc; rej = st->rej;
+    have_rp = st->have_rp != 0;
+  }
   const int S_total = (P.n_iters - P.burn_in) / P.lag;
   uint8_t *ass_out = (chain == 0) ? P.drawn + d.drawn_off : nullptr;
 
@@ -263,8 +351,6 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     return rec_next || !ok;
   };
 
-  bool have_rp = false;
-
   // the batch: group g holds the proposal of iteration m0 + g, valid while no iteration
   // from m0 on has accepted
   int m0 = 0;
@@ -305,7 +391,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
 
   // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed
   // by the initial assignment (miso.c:840-843); m >= 0 are the iterations proper.
-  for (int m = -1; m < P.n_iters; m++) {
+  for (int m = m_begin; m < m_end; m++) {
     if (!batch_ok || m - m0 >= kSpec) make_batch(m);
     const int src = 8 * (m - m0) + mi;          // this member in the group of iteration m
     if (m < 0) {
@@ -361,9 +447,19 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     have_rp = do_pass(m + 1);
   }
 
-  if (lane == 0) {
-    int *ar = P.accrej + ((long long) gene_index * P.n_chains + chain) * 2;
-    ar[0] = acc; ar[1] = rej;
+  if (m_end >= P.n_iters) {
+    if (lane == 0) {
+      int *ar = P.accrej + ((long long) gene_index * P.n_chains + chain) * 2;
+      ar[0] = acc; ar[1] = rej;
+    }
+  } else {                 // hand the chain over to whoever holds the next segment's ticket
+    if (lane < len) st->alpha[lane] = alpha;
+    if (lane < K) st->cnt[lane] = cnt_k;
+    if (lane == 0) {
+      st->rp_drawn = rp_drawn; st->n_u = n_u;
+      st->lagc = lagc; st->n_rec = n_rec; st->acc = acc; st->rej = rej;
+      st->have_rp = have_rp ? 1 : 0;
+    }
   }
 }
 
@@ -389,16 +485,22 @@ __global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? MISOB200_MINBLOCKS_CLA
   if (lane == 0 && SMEM) { mbar_init(bar, 1); fence_mbar_init(); }
   __syncthreads();
 
-  const int n_items = P.n_genes * P.n_chains;
+  const unsigned n_items = (unsigned) (P.n_genes * P.n_chains);        // work unit = one gene-chain
+  const unsigned n_pops = n_items * (unsigned) P.n_seg;
   uint32_t phase = 0;
   while (true) {
     unsigned item = 0;
-    if (lane == 0) item = atomicAdd(P.queue, 1u);
+    if (lane == 0) {
+      const unsigned p = atomicAdd(P.queue, 1u);
+      item = p < n_pops ? ring_pop(P.ring, p, n_items) : kRingEmpty;
+    }
     item = __shfl_sync(0xffffffffu, item, 0);
-    if ((int) item >= n_items) break;
-    const int gi = P.items[item / P.n_chains];
-    const int chain = (int) (item % P.n_chains);
+    if (item == kRingEmpty) break;
+    const int gi = P.items[item / (unsigned) P.n_chains];
+    const int chain = (int) (item % (unsigned) P.n_chains);
     const GeneDesc &d = P.desc[gi];
+    int *const progress = P.progress + ((long long) gi * P.n_chains + chain);
+    const int seg = *progress;
     const uint32_t tile_bytes = (uint32_t) d.tile_bytes;
     ClassRef cr;
     cr.ncls = FMT == 1 ? d.ncls : 0;
@@ -432,10 +534,17 @@ __global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? MISOB200_MINBLOCKS_CLA
       phase ^= 1u;
     }
     __syncwarp();
+    const int m_begin = seg * P.seg_len - 1;
+    const int m_end = min(m_begin + P.seg_len, P.n_iters);
     if (SMEM)
-      run_chain<K, true, WIDE, FMT>(P, d, gi, chain, TileMem<true>::base(slot), smem_u32(s_ptab), cr);
+      run_chain<K, true, WIDE, FMT>(P, d, gi, chain, TileMem<true>::base(slot), smem_u32(s_ptab), cr, m_begin, m_end);
     else
-      run_chain<K, false, WIDE, FMT>(P, d, gi, chain, TileMem<false>::base(P.tiles + d.tile_off), smem_u32(s_ptab), cr);
+      run_chain<K, false, WIDE, FMT>(P, d, gi, chain, TileMem<false>::base(P.tiles + d.tile_off), smem_u32(s_ptab), cr,
+                                     m_begin, m_end);
+    if (m_end < P.n_iters) {
+      __syncwarp();
+      if (lane == 0) { *progress = seg + 1; ring_push(P.ring, P.ring_tail, item); }
+    }
   }
 }
 

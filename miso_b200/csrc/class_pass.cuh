@@ -111,6 +111,7 @@ __device__ __forceinline__ bool thr_update(const ClassRef &cr, uint32_t ptab_s, 
   constexpr int NT = Thr<K>::NT;
   const int lane = threadIdx.x & 31;
   bool bad = false;
+  __syncwarp();          // the previous pass's threshold loads (other lanes) before these stores
   for (int c = lane; c < cr.ncls; c += 32) {
     uint4 rec;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w) : "r"(cr.rec_s + 16u * c));

@@ -69,6 +69,7 @@ __device__ __forceinline__ uint32_t quad_thr_update(bool need, const ClassRef &c
   const int o3 = o2 + __shfl_sync(kFull, n_mine, 16);
   const int total = o3 + __shfl_sync(kFull, n_mine, 24);
   uint32_t declined = 0;
+  __syncwarp();          // the previous pass's threshold loads (other lanes) before these stores
   for (int base = 0; base < total; base += 32) {
     const int p = base + lane;
     const bool on = p < total;
@@ -160,7 +161,10 @@ __device__ __forceinline__ void quad_pass(uint32_t a0, uint32_t a_end, int my_st
     a += 32;
     uint32_t uc01 = 0, uc23 = 0;
     if (MODE == 1) {
-      const int w = uw < row_last ? uw : row_last;      // clamp like the id row (those ids are null)
+      // clamp like the id row (the ids there are null, the codes are never used); the 16-bit
+      // row is read 16 bytes at a time and ends 16 bytes after 2 * padded
+      const int lim = WIDE ? row_last - 2 : row_last;
+      const int w = uw < lim ? uw : lim;
       if (!WIDE) {
         uc01 = __byte_perm(ldg_u32(ucode + 4 * w), ldg_u32(ucode + 4 * w + 4), sel);
       } else {
@@ -307,8 +311,11 @@ __device__ __noinline__ void quad_literal(unsigned gmask, uint32_t rows, const u
 // ---- the kernel ---------------------------------------------------------------------
 // Shared memory per warp: [mbarrier 16 B | 4 x slot (core tile) | 4 x {L_k 32 B, threshold planes}].
 // slot_bytes is 32 mod 128, so the four groups' id words of one step sit in different banks.
+#ifndef MISOB200_MINBLOCKS_QUAD
+#define MISOB200_MINBLOCKS_QUAD 4
+#endif
 template <int K, int WARPS, bool WIDE>
-__global__ void __launch_bounds__(WARPS * 32, 4) quad_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(WARPS * 32, MISOB200_MINBLOCKS_QUAD) quad_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int len = K - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -325,19 +332,34 @@ __global__ void __launch_bounds__(WARPS * 32, 4) quad_kernel(const __grid_consta
   __syncwarp();
 
   const int n_items = P.n_genes * P.n_chains;
+  const unsigned n_units = (unsigned) (n_items + kQuad - 1) / kQuad;    // work unit = four consecutive gene-chains
+  const unsigned n_pops = n_units * (unsigned) P.n_seg;
   const int S_total = (P.n_iters - P.burn_in) / P.lag;
   uint32_t phase = 0;
   while (true) {
-    unsigned item0 = 0;
-    if (lane == 0) item0 = atomicAdd(P.queue, (unsigned) kQuad);
-    item0 = __shfl_sync(kFull, item0, 0);
-    if ((int) item0 >= n_items) break;
+    unsigned unit = 0;
+    if (lane == 0) {
+      const unsigned p = atomicAdd(P.queue, 1u);
+      unit = p < n_pops ? ring_pop(P.ring, p, n_units) : kRingEmpty;
+    }
+    unit = __shfl_sync(kFull, unit, 0);
+    if (unit == kRingEmpty) break;
+#ifdef MISOB200_SEG_DEBUG
+    const long long dbg_t0 = clock64();
+#endif
+    const int item0 = (int) unit * kQuad;
     // a group without an item of its own shadows the last one and writes nothing
-    const bool live = (int) item0 + grp < n_items;
-    const int item = live ? (int) item0 + grp : n_items - 1;
+    const bool live = item0 + grp < n_items;
+    const int item = live ? item0 + grp : n_items - 1;
     const int gi = P.items[item / P.n_chains];
     const int chain = item % P.n_chains;
     const GeneDesc &d = P.desc[gi];
+    ChainState *const st = P.state + ((long long) gi * P.n_chains + chain);
+    int *const progress = P.progress + ((long long) gi * P.n_chains + chain);
+    const int seg = *progress;                 // the same for the four chains of a unit
+    const int m_begin = seg * P.seg_len - 1;
+    const int m_end = min(m_begin + P.seg_len, P.n_iters);
+    const bool fresh = seg == 0;
 
     ClassRef cr;
     cr.ncls = d.ncls;
@@ -384,7 +406,10 @@ __global__ void __launch_bounds__(WARPS * 32, 4) quad_kernel(const __grid_consta
     // ---- start state, splicing_drift_proposal_init (miso.c:330-447) ----------
     unsigned long long n_u = 0;
     double alpha;
-    if (P.start == MISOB200_START_AUTO) {
+    if (!fresh) {
+      alpha = st->alpha[mi < len ? mi : 0];
+      n_u = st->n_u;
+    } else if (P.start == MISOB200_START_AUTO) {
       if (K == 2) { n_u = 1; alpha = 0.0; }     // one uniform drawn and discarded (miso.c:365)
       else alpha = 1.0 / (K - 1);
     } else if (P.start == MISOB200_START_RANDOM) {
@@ -407,10 +432,17 @@ __global__ void __launch_bounds__(WARPS * 32, 4) quad_kernel(const __grid_consta
     int lagc = 0, n_rec = 0, acc = 0, rej = 0;
     int thr_state = 0;       // 0 thresholds stale (psi changed), 1 valid, 2 declined for this psi
     bool have_rp = false;
+    if (!fresh) {            // resume: the current point is a function of alpha (ChainState)
+      cur = derive<K>(alpha, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
+      cnt_k = st->cnt[kk];
+      rp_drawn = st->rp_drawn;
+      lagc = st->lagc; n_rec = st->n_rec; acc = st->acc; rej = st->rej;
+      have_rp = st->have_rp != 0;
+    }
 
     // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed by the
     // initial assignment (miso.c:840-843); m >= 0 are the iterations proper.
-    for (int m = -1; m < P.n_iters; m++) {
+    for (int m = m_begin; m < m_end; m++) {
       // ---- propose (miso.c:851): alphaNew = alpha + sd * N(0,1); normals (m+1)(K-1) .. +K-2
       const double z = stream_normal((uint32_t) (m + 1) * (uint32_t) len + (uint32_t) (mi < len ? mi : 0), gid,
                                      (uint32_t) chain, key);
@@ -519,9 +551,27 @@ __global__ void __launch_bounds__(WARPS * 32, 4) quad_kernel(const __grid_consta
       }
     }
 
-    if (mi == 0 && live) {
-      int *ar = P.accrej + ((long long) gi * P.n_chains + chain) * 2;
-      ar[0] = acc; ar[1] = rej;
+#ifdef MISOB200_SEG_DEBUG
+    if (lane == 0) atomicAdd(&g_seg_dbg[4 + (seg < 3 ? seg : 3)], (unsigned long long) (clock64() - dbg_t0));
+#endif
+    if (m_end >= P.n_iters) {
+      if (mi == 0 && live) {
+        int *ar = P.accrej + ((long long) gi * P.n_chains + chain) * 2;
+        ar[0] = acc; ar[1] = rej;
+      }
+    } else if (live) {       // hand the chain over to whoever holds the next segment's ticket
+      if (mi < len) st->alpha[mi] = alpha;
+      if (mi < K) st->cnt[mi] = cnt_k;
+      if (mi == 0) {
+        st->rp_drawn = rp_drawn; st->n_u = n_u;
+        st->lagc = lagc; st->n_rec = n_rec; st->acc = acc; st->rej = rej;
+        st->have_rp = have_rp ? 1 : 0;
+      }
+      if (mi == 0) *progress = seg + 1;
+    }
+    if (m_end < P.n_iters) {
+      __syncwarp();
+      if (lane == 0) ring_push(P.ring, P.ring_tail, unit);
     }
   }
 }

@@ -53,6 +53,12 @@ struct DevState {
   uint8_t *d_drawn = nullptr;
   int *d_accrej = nullptr;
   unsigned *d_queue = nullptr;
+  ChainState *d_state = nullptr;    // chain segments: hand-over records, progress counters, ready queues
+  int *d_progress = nullptr;
+  unsigned *d_ring = nullptr, *d_ring_tail = nullptr;
+  size_t ring_cap = 0;              // entries
+  int last_n_seg = 1;               // segments of the bucket launched last
+  double last_fill = 0;             // ... and the share of the machine its grid takes
   int *d_items = nullptr;
   std::vector<int> items[kBuckets];
   int item_off[kBuckets + 1] = {};
@@ -106,7 +112,8 @@ static void free_dev(DevState *st) {
   cudaSetDevice(st->device);
   cudaFree(st->d_tiles); cudaFree(st->d_desc); cudaFree(st->d_ptab); cudaFree(st->d_neglog); cudaFree(st->d_samples);
   cudaFree(st->d_loglik); cudaFree(st->d_summary); cudaFree(st->d_drawn); cudaFree(st->d_accrej);
-  cudaFree(st->d_queue); cudaFree(st->d_items);
+  cudaFree(st->d_queue); cudaFree(st->d_items); cudaFree(st->d_state); cudaFree(st->d_progress);
+  cudaFree(st->d_ring); cudaFree(st->d_ring_tail);
   for (auto &e : st->ev) if (e) cudaEventDestroy(e);
   for (auto &e : st->kdone) if (e) cudaEventDestroy(e);
   for (auto &e : st->kbeg) if (e) cudaEventDestroy(e);
@@ -256,6 +263,9 @@ int upload(Plan &plan, const misob200_params_t &p) {
   CK(cudaMalloc(&st->d_drawn, std::max<long long>(plan.n_drawn, 16)));
   CK(cudaMalloc(&st->d_accrej, std::max<size_t>(G, 1) * p.n_chains * 2 * sizeof(int)));
   CK(cudaMalloc(&st->d_queue, kBuckets * sizeof(unsigned)));
+  CK(cudaMalloc(&st->d_state, std::max<size_t>(G, 1) * p.n_chains * sizeof(ChainState)));
+  CK(cudaMalloc(&st->d_progress, std::max<size_t>(G, 1) * p.n_chains * sizeof(int)));
+  CK(cudaMalloc(&st->d_ring_tail, kBuckets * sizeof(unsigned)));
   CK(cudaMalloc(&st->d_items, std::max(total, 1) * sizeof(int)));
 
   // pin the plan's arenas once so the per-run H2D runs at link speed
@@ -268,6 +278,34 @@ int upload(Plan &plan, const misob200_params_t &p) {
   st->h_accrej.resize(std::max<size_t>(G, 1) * p.n_chains * 2);
   if (cudaHostRegister(st->h_drawn.data(), st->h_drawn.size(), cudaHostRegisterDefault) != cudaSuccess) cudaGetLastError();
   return copy_inputs(plan, st);
+}
+
+// Steps per chain segment (ChainState in chain_kernel.cuh).  256 keeps the per-segment overhead
+// (tile reload, re-derived current point, thresholds) near 1 % and a bucket's tail to the time of
+// 256 iterations; MISOB200_SEG_ITERS overrides (tests use odd small values).
+static int segment_length(const DevState *st) {
+  const char *e = std::getenv("MISOB200_SEG_ITERS");
+  int len = e ? std::atoi(e) : 256;
+  const int steps = st->params.n_iters + 1;
+  if (len < 1 || len > steps) len = steps;
+  return len;
+}
+// `n_units` work units on `n_warps` resident warps.  With at most one unit per warp there is
+// nothing to balance, every chain is in flight from start to end; chains are only cut when the
+// bucket needs more than one wave.  (Measured: in the one-wave regime hand-overs made the quad
+// kernel's resumed segments run up to 2x slower, profiles/README.md "segments".)
+static void set_segments(ChainParams &P, DevState *st, int b, long long n_units, long long n_warps) {
+  const int steps = st->params.n_iters + 1;
+  P.seg_len = segment_length(st);
+  if (n_units <= n_warps && !std::getenv("MISOB200_SEG_ALWAYS")) P.seg_len = steps;
+  P.n_seg = (steps + P.seg_len - 1) / P.seg_len;
+  st->last_n_seg = P.n_seg;
+  st->last_fill = (double) n_warps / (4.0 * 4 * st->sm_count);      // share of the resident warps (4 CTAs x 4 warps per SM)
+  P.state = st->d_state;
+  P.progress = st->d_progress;
+  // bucket b's ring: room for one push per (gene-chain, segment)
+  P.ring = st->d_ring + (size_t) st->item_off[b] * st->params.n_chains * P.n_seg;
+  P.ring_tail = st->d_ring_tail + b;
 }
 
 template <int K, int FMT>
@@ -334,6 +372,7 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;
   P.thr_bytes = thr;
+  set_segments(P, st, b, n_items, blocks * WARPS);
   kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[b]>>>(P);
   CK(cudaGetLastError());
   (*launches)++;
@@ -402,6 +441,7 @@ static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;
   P.thr_bytes = thr;
+  set_segments(P, st, b, (n_items + kQuad - 1) / kQuad, blocks * WARPS);
   kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[b]>>>(P);
   if (cudaGetLastError() != cudaSuccess) { set_error("quad kernel launch failed"); return 1; }
   (*launches)++;
@@ -442,6 +482,22 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
   CK(cudaSetDevice(st->device));
   int nl = 0;
   CK(cudaMemsetAsync(st->d_queue, 0, kBuckets * sizeof(unsigned), st->stream));
+  CK(cudaMemsetAsync(st->d_progress, 0, std::max<size_t>(plan.desc.size(), 1) * st->params.n_chains * sizeof(int), st->stream));
+  {
+    // ready queues of the chain segments: all slots empty, no pushes yet
+    const int seg_len = segment_length(st);
+    const size_t n_seg = (size_t) (st->params.n_iters + seg_len) / seg_len;
+    const size_t need = std::max<size_t>((size_t) st->item_off[kBuckets] * st->params.n_chains * n_seg, 1);
+    if (need > st->ring_cap) {
+      CK(cudaStreamSynchronize(st->stream));
+      cudaFree(st->d_ring);
+      st->d_ring = nullptr;
+      CK(cudaMalloc(&st->d_ring, need * sizeof(unsigned)));
+      st->ring_cap = need;
+    }
+    CK(cudaMemsetAsync(st->d_ring, 0xff, need * sizeof(unsigned), st->stream));
+    CK(cudaMemsetAsync(st->d_ring_tail, 0, kBuckets * sizeof(unsigned), st->stream));
+  }
   // recorded samples that a short chain never writes stay zero, like the
   // reference's zero-initialised sample matrix
   CK(cudaMemsetAsync(st->d_samples, 0, std::max<long long>(st->n_samples, 1) * sizeof(double), st->stream));
@@ -452,7 +508,8 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
   // other genes' outputs are then left unset
   const char *only = std::getenv("MISOB200_ONLY_K");
   const int only_k = only ? std::atoi(only) : 0;
-  const bool serial = std::getenv("MISOB200_SERIAL") != nullptr;
+  const bool serial = std::getenv("MISOB200_SERIAL") != nullptr;                 // development knobs
+  const bool concurrent_all = std::getenv("MISOB200_CONCURRENT") != nullptr;
   // chains per warp: four (quad_kernel.cuh) once there are enough gene-chains to fill the
   // machine that way, else one (chain_kernel.cuh: a chain alone on a warp finishes sooner).
   // MISOB200_CHAINS_PER_WARP = 1 | 4 overrides (tests run both).
@@ -466,25 +523,40 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
   }
   int prev = -1;
   // dense buckets first (slowest per read), big K before small K (longest chains)
+  const bool small_first = std::getenv("MISOB200_SMALL_K_FIRST") != nullptr;
   for (int fmt = 0; fmt < 2 && !rc; fmt++)
-    for (int k = kMaxIso; k >= 2 && !rc; k--) {
+    for (int kk = kMaxIso; kk >= 2 && !rc; kk--) {
+      const int k = small_first ? kMaxIso + 2 - kk : kk;
       const int b = fmt * (kMaxIso + 1) + k;
       if (st->items[b].empty()) continue;
       if (only_k && k != only_k) continue;
       CK(cudaStreamWaitEvent(st->kstream[b], st->ev[2], 0));
-      if (serial && prev >= 0) CK(cudaStreamWaitEvent(st->kstream[b], st->kdone[prev], 0));
-      prev = b;
+      // A bucket that fills most of the machine runs alone and the next one starts after it: two
+      // different kernels sharing the SMs cost more than the idle share and the tail -- short,
+      // when the bucket is cut into segments (measured, profiles/r1_ab10/ab11).  Small buckets
+      // overlap with each other.
+      if (prev >= 0 && !concurrent_all) CK(cudaStreamWaitEvent(st->kstream[b], st->kdone[prev], 0));
       CK(cudaEventRecord(st->kbeg[b], st->kstream[b]));
       if (!(fmt && quad && launch_quad_k(plan, st, k, &nl, &rc)))
         rc = fmt ? launch_k<1>(plan, st, k, &nl) : launch_k<0>(plan, st, k, &nl);
       if (rc) return rc;
       CK(cudaEventRecord(st->kend[b], st->kstream[b]));
       CK(cudaEventRecord(st->kdone[b], st->kstream[b]));
+      if (serial || st->last_n_seg > 1 || st->last_fill >= 0.6) prev = b;
       CK(cudaStreamWaitEvent(st->stream, st->kdone[b], 0));
     }
   CK(cudaEventRecord(st->ev[3], st->stream));
   CK(cudaStreamSynchronize(st->stream));
   CK(cudaGetLastError());
+#ifdef MISOB200_SEG_DEBUG
+  {
+    unsigned long long h[8] = {0}, z[8] = {0};
+    cudaMemcpyFromSymbol(h, g_seg_dbg, sizeof(h));
+    cudaMemcpyToSymbol(g_seg_dbg, z, sizeof(z));
+    fprintf(stderr, "[seg debug] polls %llu wait Mcycles %.1f pops %llu ring pops %llu; Mcycles in segment 0/1/2/3+: %.0f %.0f %.0f %.0f\n",
+            h[0], h[1] / 1e6, h[2], h[3], h[4] / 1e6, h[5] / 1e6, h[6] / 1e6, h[7] / 1e6);
+  }
+#endif
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, st->ev[2], st->ev[3]));
   if (kernel_ms) *kernel_ms = ms;

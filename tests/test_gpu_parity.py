@@ -34,6 +34,10 @@ def chains_per_warp(request, monkeypatch):
 @pytest.fixture(params=LAYOUTS)
 def tile_format(request, monkeypatch):
     monkeypatch.setenv("MISOB200_CHAINS_PER_WARP", "4" if request.param == "quad" else "1")
+    # chains are handed from warp to warp in segments (ChainState, chain_kernel.cuh): an odd short
+    # segment makes every chain resume many times, at every phase of the lag counter
+    monkeypatch.setenv("MISOB200_SEG_ITERS", "37")
+    monkeypatch.setenv("MISOB200_SEG_ALWAYS", "1")      # (by default only buckets of more than one wave are cut)
     return 0 if request.param == "dense" else -1
 
 
@@ -139,3 +143,23 @@ def test_start_random_and_uniform(mb, port, kind, chains_per_warp):
         for g in range(16):
             want = oracle_gene(port, w.gene(g), kind == 1, params, gene_id=40 + g)
             assert_gene_parity(plan.gene_result(out, g), want, tag="start %d kind %d gene %d" % (start, kind, g))
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_results_do_not_depend_on_segment_length(mb, kind, chains_per_warp, monkeypatch):
+    """Cutting the chains into segments (resume from ChainState) must not change a single bit."""
+    w = mb.Workload(kind, 37, 400, 36, 250.0, 900.0, 4.0, seed=23)
+    plan = mb.Plan().append(w)
+    params = mb.make_params(n_iters=500, burn_in=100, lag=7, n_chains=3, seed=4)
+    ref = None
+    monkeypatch.setenv("MISOB200_SEG_ALWAYS", "1")          # (by default only buckets of more than one wave are cut)
+    for seg in ("1000000", "256", "50", "7", "1"):
+        monkeypatch.setenv("MISOB200_SEG_ITERS", seg)
+        out = plan.run(params)
+        got = {k: np.array(out[k], copy=True) for k in ("samples", "loglik", "assignment", "rundata")}
+        if ref is None:
+            ref = got
+            assert (got["rundata"][:, 5] + got["rundata"][:, 6] == 1500).all()
+        else:
+            for k in ref:
+                np.testing.assert_array_equal(got[k], ref[k], err_msg="seg %s %s" % (seg, k))
