@@ -163,3 +163,46 @@ def test_results_do_not_depend_on_segment_length(mb, kind, chains_per_warp, monk
         else:
             for k in ref:
                 np.testing.assert_array_equal(got[k], ref[k], err_msg="seg %s %s" % (seg, k))
+
+
+def test_degenerate_genes_in_one_batch(mb, port, chains_per_warp):
+    """One batch mixing degenerate inputs: no reads at all (the chain runs on the prior; defined by
+    the port only -- the reference C aborts on an empty read set, error.c:121, and misopy never
+    passes one, miso_sampler.py:229), reads that fit no isoform (assignment -1, miso.c:65), a
+    gene whose reads all hit the same two isoforms (a single class), a bad CIGAR (status EINVAL,
+    the other genes unaffected), shorter-than-read-length alignments (all-zero column,
+    solve.c:55), an ordinary gene, and non-flat hyperparameters."""
+    ex = ((1, 100), (201, 300), (401, 500))
+    iso = ((0, 1, 2), (0, 2), (0, 1))
+    g = mb.Gene(ex, iso)
+    rng = np.random.default_rng(3)
+    inc2 = [int(p) for p in rng.integers(210, 260, 40)]          # inside exon 1: isoforms 0 and 2
+    only0 = [95] * 25                                           # junction exon 0 -> 1 (6M100N27M): isoforms 0 and 2
+    nowhere = [120] * 10                                        # intron
+    ordinary_pos = inc2 + [int(p) for p in rng.integers(1, 60, 50)] + [int(p) for p in rng.integers(405, 460, 30)]
+    cases = [
+        ([], []),
+        (nowhere, ["33M"] * len(nowhere)),
+        (only0, ["6M100N27M"] * len(only0)),
+        ([10], ["33Q"]),
+        (inc2, ["30M"] * len(inc2)),
+        (ordinary_pos, ["33M"] * len(ordinary_pos)),
+        (ordinary_pos, ["33M"] * len(ordinary_pos)),
+    ]
+    hyper = [None] * 6 + [(0.5, 2.0, 1.5)]
+    rb = mb.ReadBatch([g] * len(cases), [c[0] for c in cases], [c[1] for c in cases], 33,
+                      hyper=[h if h is not None else (1.0, 1.0, 1.0) for h in hyper])
+    plan = mb.Plan().append(rb)
+    params = mb.make_params(n_iters=300, burn_in=50, lag=5, n_chains=2, seed=12)
+    out = plan.run(params)
+    assert [int(s) for s in out["status"]] == [0, 0, 0, 4, 0, 0, 0]
+    for i, (pos, cig) in enumerate(cases):
+        r = plan.gene_result(out, i)
+        if i == 3:
+            assert (r["assignment"] == -1).all()
+            continue
+        want = oracle_gene(port, (ex, iso, np.asarray(pos, np.int32), cig), False, params, gene_id=i,
+                           read_len=33, hyper=hyper[i])
+        assert_gene_parity(r, want, tag="degenerate case %d" % i)
+    assert (plan.gene_result(out, 1)["assignment"] == -1).all()
+    assert (plan.gene_result(out, 4)["assignment"] == -1).all()

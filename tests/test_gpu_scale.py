@@ -95,3 +95,25 @@ def test_two_sample_bayes_factor_on_device(mb):
     assert (pa.info()[:, 0] != pc.info()[:, 0]).any()
     with pytest.raises(mb.InternalError, match="different number of isoforms"):
         pa.compare(pc)
+
+
+def test_segment_hand_over_at_scale(mb, monkeypatch):
+    """Thousands of chains handed from warp to warp through the ready queues, several waves per
+    bucket and buckets of less than a wave alike: outputs identical to the uncut run, every
+    chain complete.  (tools/seg_verify.py is the same check at the full cfg-3 size.)"""
+    w = mb.Workload(1, 12000, 600, 36, 250.0, 900.0, 4.0, seed=77)
+    plan = mb.Plan().append(w)
+    params = mb.make_params(1200, 200, 10, 1, seed=6)
+    res = {}
+    for name, env in (("uncut", {"MISOB200_SEG_ITERS": "100000000"}),
+                      ("cut", {"MISOB200_SEG_ITERS": "64", "MISOB200_SEG_ALWAYS": "1"}),
+                      ("default", {"MISOB200_SEG_ITERS": "64"})):
+        monkeypatch.delenv("MISOB200_SEG_ALWAYS", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = plan.run(params)
+        res[name] = {k: np.array(out[k], copy=True) for k in ("samples", "loglik", "assignment", "rundata")}
+        assert (res[name]["rundata"][:, 5] + res[name]["rundata"][:, 6] == 1200).all(), name
+    for name in ("cut", "default"):
+        for k in res["uncut"]:
+            np.testing.assert_array_equal(res[name][k], res["uncut"][k], err_msg="%s %s" % (name, k))
