@@ -400,7 +400,7 @@ static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
     for (int g : v) r2 += plan.desc[g].R2;
     const char *lim = std::getenv("MISOB200_QUAD_MAX_READS");
     const char *cpw = std::getenv("MISOB200_CHAINS_PER_WARP");      // "4": tests force the layout
-    const long long max_mean = lim ? std::atoll(lim) : (cpw && std::atoi(cpw) == 4) ? (1LL << 40) : 1600;
+    const long long max_mean = lim ? std::atoll(lim) : (cpw && std::atoi(cpw) == 4) ? (1LL << 40) : 1200;
     if (!v.empty() && r2 > max_mean * (long long) v.size()) return 0;
   }
   const int slot = ((core + 127) & ~127) + 32;     // 32 mod 128: the four groups' id words fall in different banks
