@@ -125,6 +125,16 @@ int misob200_plan_create(misob200_plan_t **plan);
 int misob200_plan_destroy(misob200_plan_t *plan);
 int misob200_plan_append(misob200_plan_t *plan, const misob200_reads_t *reads,
 			 int n_threads);
+/* the same, with the read <-> isoform compatibility (splicing_matchIso[_paired]
+   + splicing_parse_cigar, src/solve.c:8-306) computed by a kernel on `device`
+   instead of the host threads; identical plan, MISOB200_ECUDA without a GPU */
+int misob200_plan_append_device(misob200_plan_t *plan,
+				const misob200_reads_t *reads, int n_threads,
+				int device);
+/* timing / traffic of the calling thread's last device matching:
+   kernel, H2D, D2H in ms; input and output bytes */
+int misob200_last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms,
+			      int64_t *bytes_in, int64_t *bytes_out);
 
 /* keep the code matrix and draw order of later appends for
    misob200_plan_gene_match (parity tests; costs 4 bytes per read x isoform) */

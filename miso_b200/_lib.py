@@ -62,6 +62,8 @@ def _load():
     lib.misob200_plan_tile_format.argtypes = [vp, C.c_int]
     lib.misob200_plan_gene_tile.argtypes = [vp, C.c_int32, vp, vp, vp]
     lib.misob200_plan_append.argtypes = [vp, C.POINTER(Reads), C.c_int]
+    lib.misob200_plan_append_device.argtypes = [vp, C.POINTER(Reads), C.c_int, C.c_int]
+    lib.misob200_last_match_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.misob200_plan_size.argtypes = [vp, vp, vp, vp]
     lib.misob200_plan_gene_info.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.misob200_plan_gene_classes.argtypes = [vp, C.c_int32, vp, vp]
@@ -96,7 +98,8 @@ lib = _load()
 EXPORTS = [
     "misob200_version", "misob200_last_error", "misob200_init", "misob200_shutdown",
     "misob200_device_count", "misob200_plan_create", "misob200_plan_destroy",
-    "misob200_plan_append", "misob200_plan_keep_match", "misob200_plan_size",
+    "misob200_plan_append", "misob200_plan_append_device", "misob200_last_match_stats",
+    "misob200_plan_keep_match", "misob200_plan_size",
     "misob200_plan_tile_format", "misob200_plan_gene_tile",
     "misob200_plan_gene_info", "misob200_plan_gene_classes", "misob200_plan_gene_match",
     "misob200_plan_fragment_table", "misob200_plan_offsets", "misob200_plan_output_sizes",

@@ -174,11 +174,25 @@ class Plan:
             check(lib.misob200_plan_tile_format(self.h, tile_format))
         self._info = None
 
-    def append(self, reads, n_threads=0):
+    def append(self, reads, n_threads=0, match_device=None):
+        """Setup stage for a batch (a-12 ... a-18).  ``match_device``: GPU ordinal that computes
+        the read <-> isoform compatibility (csrc/match.cu) instead of the host threads."""
         struct = reads.struct if hasattr(reads, "struct") else reads
-        check(lib.misob200_plan_append(self.h, C.byref(struct), n_threads))
+        if match_device is None:
+            check(lib.misob200_plan_append(self.h, C.byref(struct), n_threads))
+        else:
+            check(lib.misob200_plan_append_device(self.h, C.byref(struct), n_threads, int(match_device)))
         self._info = None
         return self
+
+    @staticmethod
+    def last_match_stats():
+        """(kernel ms, H2D ms, D2H ms, bytes in, bytes out) of the last device matching."""
+        k, h, d = C.c_double(), C.c_double(), C.c_double()
+        bi, bo = C.c_int64(), C.c_int64()
+        check(lib.misob200_last_match_stats(C.addressof(k), C.addressof(h), C.addressof(d), C.addressof(bi),
+                                            C.addressof(bo)))
+        return k.value, h.value, d.value, bi.value, bo.value
 
     def close(self):
         if self.h:

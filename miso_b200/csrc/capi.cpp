@@ -71,6 +71,19 @@ int misob200_plan_append(misob200_plan_t *plan, const misob200_reads_t *reads, i
   if (plan->p.dev) release_device(plan->p);
   return plan_append(plan->p, *reads, n_threads);
 }
+int misob200_plan_append_device(misob200_plan_t *plan, const misob200_reads_t *reads, int n_threads, int device) {
+  if (!plan || !reads) { set_error("plan_append_device: null argument"); return MISOB200_EINVAL; }
+  if (device < 0) { set_error("plan_append_device: device ordinal out of range"); return MISOB200_EINVAL; }
+  if (plan->p.dev) release_device(plan->p);
+  return plan_append(plan->p, *reads, n_threads, device);
+}
+int misob200_last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, int64_t *bytes_in, int64_t *bytes_out) {
+  long long bi = 0, bo = 0;
+  last_match_stats(kernel_ms, h2d_ms, d2h_ms, &bi, &bo);
+  if (bytes_in) *bytes_in = bi;
+  if (bytes_out) *bytes_out = bo;
+  return 0;
+}
 int misob200_plan_size(const misob200_plan_t *plan, int32_t *n_genes, int64_t *n_reads, int64_t *tile_bytes) {
   if (!plan) return MISOB200_EINVAL;
   if (n_genes) *n_genes = (int32_t) plan->p.desc.size();

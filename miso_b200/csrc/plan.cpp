@@ -14,6 +14,7 @@
 //     McIlroy's "Engineering a Sort Function" (the reference runs it from
 //     src/qsort.c through include/matrix.pmt:579-589).
 #include "plan.hpp"
+#include "match_core.hpp"
 
 #include <algorithm>
 #include <array>
@@ -28,82 +29,6 @@
 namespace misob200 {
 
 namespace {
-
-struct IsoView {          // one gene's isoforms
-  int K;
-  const int32_t *exon_off;   // K+1 entries, absolute
-  const int32_t *ex_start, *ex_end;
-};
-
-// ---- CIGAR ------------------------------------------------------------
-// Semantics of splicing_parse_cigar (src/solve.c:220-306): M = X S H D are
-// match-like and clipped to read_len in total, N is an intron (negative),
-// I is skipped, S/H only at the ends, anything else is an error.
-struct Cigar {
-  int n = 0, len = 0;
-  int op[64];
-};
-
-int parse_cigar(const char *s, int read_len, Cigar &out) {
-  int mode = 0;
-  out.n = 0; out.len = 0;
-  while (*s) {
-    char *end;
-    long l = strtol(s, &end, 10);
-    char c = *end;
-    const bool clip = (c == 'S' || c == 'H');
-    if (mode == 0 && !clip) mode = 1;
-    else if (mode == 1 && clip) mode = 2;
-    else if (mode == 2 && !clip) return MISOB200_EINVAL;
-    if (c == 'M' || c == '=' || c == 'X' || clip || c == 'D') {
-      if (read_len > 0 && out.len + l > read_len) l = read_len - out.len;
-      if (out.n >= 64) return MISOB200_EINVAL;
-      out.op[out.n++] = (int) l;
-      out.len += (int) l;
-    } else if (c == 'N') {
-      if (out.n >= 64) return MISOB200_EINVAL;
-      out.op[out.n++] = (int) -l;
-    } else if (c == 'I') {
-      // not on the genome: nothing to do
-    } else {
-      return MISOB200_EINVAL;   // also hit by a trailing number without a letter
-    }
-    s = end + 1;
-  }
-  return 0;
-}
-
-// 1 if the read's blocks tile isoform k's exons from pos (src/solve.c:65-95)
-inline int compatible(const IsoView &g, int k, int pos, const Cigar &cg) {
-  int ex = g.exon_off[k];
-  const int ex_hi = g.exon_off[k + 1];
-  while (ex < ex_hi && (pos < g.ex_start[ex] || g.ex_end[ex] < pos)) ex++;
-  if (ex >= ex_hi) return 0;
-  for (int c = 0; c < cg.n; c++) {
-    const int o = cg.op[c];
-    if (o > 0) {
-      if (pos + o - 1 > g.ex_end[ex]) return 0;
-      pos += o;
-    } else {
-      if (pos != g.ex_end[ex] + 1) return 0;
-      pos -= o;
-      ex++;
-      if (ex >= ex_hi || pos != g.ex_start[ex]) return 0;
-    }
-  }
-  return 1;
-}
-
-// position on the spliced isoform, 1-based, or -1 (src/gff.c:855-900,1041-1084)
-inline int iso_coordinate(const IsoView &g, int k, int pos) {
-  int before = 0;
-  for (int ex = g.exon_off[k]; ex < g.exon_off[k + 1]; ex++) {
-    if (g.ex_end[ex] < pos) { before += g.ex_end[ex] - g.ex_start[ex] + 1; continue; }
-    if (g.ex_start[ex] <= pos) return pos - g.ex_start[ex] + 1 + before;
-    return -1;
-  }
-  return -1;
-}
 
 // ---- Bentley-McIlroy index sort -----------------------------------------
 template <class Cmp>
@@ -187,7 +112,7 @@ struct GeneOut {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &out) {
+void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &out, const DeviceCodes *pre) {
   GeneHost &h = out.h;
   GeneDesc &d = out.d;
   std::memset(&d, 0, sizeof(d));
@@ -216,31 +141,20 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   }
 
   // ---- compatibility codes, K x R column-major --------------------------
+  // match_core.hpp; either computed here, or taken from the device kernel (match.cu), which
+  // compiles the same functions
   std::vector<int32_t> codes((size_t) K * (R > 0 ? R : 1), 0);
-  Cigar cg, cg2;
-  for (int r = 0; r < R; r++) {
-    int32_t *col = codes.data() + (size_t) r * K;
-    if (!paired) {
-      const long long ri = r0 + r;
-      if (parse_cigar(in.cigar + in.cigar_off[ri], in.read_len, cg)) { h.status = MISOB200_EINVAL; return; }
-      if (cg.n == 0 || cg.len < in.read_len || cg.op[0] < overhang || cg.op[cg.n - 1] < overhang) continue;
-      for (int k = 0; k < K; k++) col[k] = compatible(gv, k, in.position[ri], cg);
-    } else {
-      const long long r1 = r0 + 2LL * r, r2 = r1 + 1;
-      if (parse_cigar(in.cigar + in.cigar_off[r1], in.read_len, cg) ||
-          parse_cigar(in.cigar + in.cigar_off[r2], in.read_len, cg2)) { h.status = MISOB200_EINVAL; return; }
-      const bool ok1 = !(cg.n == 0 || cg.len < in.read_len || cg.op[0] < overhang || cg.op[cg.n - 1] < overhang);
-      const bool ok2 = !(cg2.n == 0 || cg2.len < in.read_len || cg2.op[0] < overhang || cg2.op[cg2.n - 1] < overhang);
-      if (!ok1 || !ok2) continue;
-      const int p1 = in.position[r1], p2 = in.position[r2];
-      for (int k = 0; k < K; k++) {
-        if (!compatible(gv, k, p1, cg) || !compatible(gv, k, p2, cg2)) continue;
-        // src/solve.c:190-198
-        const int frag = iso_coordinate(gv, k, p2) - iso_coordinate(gv, k, p1) + in.read_len;
-        if (frag < plan.frag_start || frag >= plan.frag_len_n + plan.frag_start) continue;
-        col[k] = frag - plan.frag_start + 1;
+  if (pre) {
+    if (pre->status[g]) { h.status = pre->status[g]; return; }
+    const uint16_t *src = pre->codes + pre->code_off[g];
+    for (size_t i = 0; i < (size_t) K * R; i++) codes[i] = src[i];
+  } else {
+    const MatchParams mp{in.read_len, overhang, paired, plan.frag_start, plan.frag_len_n};
+    for (int r = 0; r < R; r++)
+      if (match_read(gv, mp, in.position + r0, in.cigar_off + r0, in.cigar, r, codes.data() + (size_t) r * K)) {
+        h.status = MISOB200_EINVAL;
+        return;
       }
-    }
   }
   // odd trailing mate of a paired batch is ignored, as noreads/2 does (solve.c:187)
 
@@ -492,7 +406,7 @@ void fragment_table(Plan &plan) {
 
 }  // namespace
 
-int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads) {
+int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match_device) {
   if (in.n_genes < 0 || !in.iso_off || !in.exon_off || !in.read_off) {
     set_error("plan_append: null or negative input"); return MISOB200_EINVAL;
   }
@@ -516,13 +430,22 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads) {
   if (in.read_len < 0) { set_error("plan_append: negative read length"); return MISOB200_EINVAL; }
 
   const int G = in.n_genes;
+  // optional: read <-> isoform compatibility on the GPU
+  DeviceCodes dev_codes;
+  const DeviceCodes *pre = nullptr;
+  if (match_device >= 0) {
+    const MatchParams mp{in.read_len, in.overhang == 0 ? 1 : in.overhang, paired, plan.frag_start, plan.frag_len_n};
+    const int rc = match_on_device(in, mp, match_device, dev_codes);
+    if (rc) return rc;
+    pre = &dev_codes;
+  }
   std::vector<GeneOut> outs(G);
   std::atomic<int> next(0);
   int nt = n_threads > 0 ? n_threads : (int) std::thread::hardware_concurrency();
   if (nt < 1) nt = 1;
   if (nt > G) nt = G > 0 ? G : 1;
   auto work = [&]() {
-    for (int g; (g = next.fetch_add(1)) < G;) build_gene(plan, in, g, outs[g]);
+    for (int g; (g = next.fetch_add(1)) < G;) build_gene(plan, in, g, outs[g], pre);
   };
   if (nt == 1) work();
   else {

@@ -82,7 +82,22 @@ struct Plan {
   void *dev = nullptr;
 };
 
+// Compatibility codes computed by match.cu for a whole batch (u16: codes < kMaxCodes).
+struct MatchParams;
+struct DeviceCodes {
+  std::vector<uint16_t> codes_store;
+  std::vector<long long> code_off;       // per gene: offset of its K x R block (read-major, K contiguous)
+  std::vector<int> status;               // per gene: 0 or MISOB200_EINVAL (unparsable CIGAR)
+  const uint16_t *codes = nullptr;
+  double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
+  long long bytes_in = 0, bytes_out = 0;
+};
+int match_on_device(const misob200_reads_t &reads, const MatchParams &mp, int device, DeviceCodes &out);
+// timing of the last device matching of this thread's plan_append (ms; bytes)
+void last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, long long *bytes_in, long long *bytes_out);
+
 void set_error(const std::string &msg);
-int plan_append(Plan &plan, const misob200_reads_t &reads, int n_threads);
+// match_device < 0: compatibility on the host; >= 0: on that GPU
+int plan_append(Plan &plan, const misob200_reads_t &reads, int n_threads, int match_device = -1);
 
 }  // namespace misob200

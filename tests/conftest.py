@@ -29,3 +29,12 @@ def ref():
     if not refdriver.available():
         pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
     return refdriver.RefOracle()
+
+
+@pytest.fixture(scope="session")
+def ref_or_port(request):
+    """The unmodified reference where it was built (this container), else the pinned port."""
+    import refdriver
+    if refdriver.available():
+        return refdriver.RefOracle()
+    return request.getfixturevalue("port")

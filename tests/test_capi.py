@@ -73,3 +73,14 @@ def test_argument_checks_mirror_the_reference():
         pysplicing.simulateReads(g, 0, (0.2, 0.3, 0.5), 10, 33)
     assert (pysplicing.MISO_START_AUTO, pysplicing.MISO_START_LINEAR, pysplicing.MISO_STOP_CONVERGENT_MEAN,
             pysplicing.MISO_ALGO_CLASSES) == (0, 4, 1, 2)
+
+
+def test_device_matching_fails_loudly_without_gpu():
+    """misob200_plan_append_device has no host fallback: without a GPU it is an error, the plan stays empty."""
+    if mb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    w = mb.Workload(0, 4, 50, 36, 250.0, 900.0, 4.0, seed=1)
+    p = mb.Plan()
+    with pytest.raises(mb.InternalError, match="no CUDA device"):
+        p.append(w, match_device=0)
+    assert p.size()[0] == 0

@@ -138,3 +138,40 @@ def test_wide_insert_model_plan(port):
     # an insert model too wide even for 16-bit tiles in shared memory is refused, not mis-run
     big = mb.Plan().append(mb.Workload(1, 1, 10, 36, 3000.0, 360000.0, 4.0, seed=1))
     assert big.info()[0, 4] == 12
+
+
+ODD_CIGARS = ["33M", "10M5I23M", "3S30M", "30M3S", "2H31M", "10M2D21M", "6M100N27M", "33=", "33X", " 33M", "+33M",
+              "033M", "20M", "40M", "1M100N32M", "6M100N20M100N7M", "3S3M100N27M", "0M33M"]
+
+
+def test_odd_cigars_match_the_reference(ref_or_port):
+    """CIGAR corner cases of splicing_parse_cigar (solve.c:220-306) -- insertions, clips, deletions,
+    strtol's leading blank / sign / zeros, too short, too long, zero-length blocks -- through the shared
+    matching code (csrc/match_core.hpp) against the oracle."""
+    ex = ((1, 100), (201, 300), (401, 500))
+    iso = ((0, 1, 2), (0, 2), (0, 1))
+    pos, cig = [], []
+    for c in ODD_CIGARS:
+        for p in (1, 68, 95, 98, 210, 268, 295, 405):
+            pos.append(p)
+            cig.append(c)
+    g = mb.Gene(ex, iso)
+    for overhang in (1, 4):
+        plan = mb.Plan(keep_match=True).append(mb.ReadBatch([g], [pos], [cig], 33, overhang=overhang))
+        assert plan.info()[0, 4] == 0
+        codes, order = plan.match(0)
+        want = ref_or_port.match_se(ex, iso, np.asarray(pos, np.int32), cig, 33, overhang)
+        np.testing.assert_array_equal(codes.astype(float), want["match"])
+        np.testing.assert_array_equal(order, want["order"])
+    # paired: the same strings as mates
+    ppos, pcig = [], []
+    for i in range(0, len(pos) - 1, 2):
+        ppos += [pos[i], pos[i] + 40]
+        pcig += [cig[i], cig[i + 1]]
+    plan = mb.Plan(keep_match=True).append(mb.ReadBatch([g], [ppos], [pcig], 33, paired=True, frag_mean=80.0,
+                                                        frag_var=400.0, num_devs=4.0))
+    codes, order = plan.match(0)
+    fp, fs = plan.fragment_table()
+    want = ref_or_port.match_pe(ex, iso, np.asarray(ppos, np.int32), pcig, 33, 80.0, 400.0, 4.0, 1)
+    np.testing.assert_array_equal(np.where(codes > 0, codes - 1 + fs, -1), want["fraglen"])
+    np.testing.assert_array_equal(order, want["order"])
