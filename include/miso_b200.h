@@ -103,8 +103,9 @@ typedef struct misob200_params {
 /* per-gene layout of the outputs of misob200_run (all caller-owned):
  *   samples   : for gene g, K_g x (n_chains*S) doubles, column-major, column
  *               s*n_chains + c = sample s of chain c (src/miso.c:884-888),
- *               S = (n_iters-burn_in)/lag; genes back to back at
- *               misob200_plan_sample_offset(plan, g, ...)
+ *               S = (n_iters-burn_in)/lag; the gene blocks lie back to back
+ *               in the device's run order, locate gene g with
+ *               misob200_plan_offsets(plan, params, g, ...)
  *   loglik    : n_chains*S doubles per gene, same column order
  *   assignment: one int32 per read (SE) / pair (PE) in input order, chain 0,
  *               -1 = incompatible (src/miso.c:943-946)
@@ -170,7 +171,11 @@ int misob200_plan_gene_match(const misob200_plan_t *plan, int32_t gene,
 int misob200_plan_fragment_table(const misob200_plan_t *plan, int32_t cap,
 				 double *prob, int32_t *frag_start,
 				 int32_t *n_len);
-/* offsets (in elements) of gene g inside samples / loglik / assignment */
+/* offsets (in elements) of gene g inside samples / loglik / assignment.
+   The per-gene blocks of samples and loglik are NOT in gene order: they follow
+   the order in which the device runs the genes (isoform-count buckets), so
+   that finished buckets copy out while others still run; always go through
+   this call.  assignment is in input read order. */
 int misob200_plan_offsets(const misob200_plan_t *plan,
 			  const misob200_params_t *params, int32_t gene,
 			  int64_t *sample_off, int64_t *loglik_off,

@@ -7,10 +7,11 @@
 
 namespace misob200 {
 const char *last_error();
-void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, long long *n_loglik);
+void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, long long *n_loglik,
+                 long long (*range)[4] = nullptr);
 int device_init(int device);
 int upload(Plan &plan, const misob200_params_t &p);
-int run_resident(Plan &plan, double *kernel_ms, int *launches);
+int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples = nullptr, double *h_loglik = nullptr);
 int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, int32_t *rundata,
              int32_t *status);
 int release_device(Plan &plan);
@@ -146,13 +147,12 @@ int misob200_plan_offsets(const misob200_plan_t *plan, const misob200_params_t *
                           int64_t *sample_off, int64_t *loglik_off, int64_t *assign_off) {
   if (int rc = check_gene(plan, gene)) return rc;
   if (!params || params->lag < 1) return MISOB200_EINVAL;
-  const Plan &p = plan->p;
-  const long long S = (params->n_iters - params->burn_in) / params->lag;
-  long long so = 0, lo = 0;
-  for (int g = 0; g < gene; g++) {
-    so += (long long) p.desc[g].K * params->n_chains * S;
-    lo += (long long) params->n_chains * S;
-  }
+  // the layout follows the run order of the buckets (run.cu plan_layout); offsets are derived
+  // fields of the descriptors, filled on demand
+  Plan &p = const_cast<Plan &>(plan->p);
+  long long ns = 0, nl = 0;
+  plan_layout(p, *params, &ns, &nl);
+  const long long so = p.desc[gene].sample_off, lo = p.desc[gene].loglik_off;
   if (sample_off) *sample_off = so;
   if (loglik_off) *loglik_off = lo;
   if (assign_off) *assign_off = p.host[gene].read_base;
@@ -196,8 +196,10 @@ int misob200_run(misob200_plan_t *plan, const misob200_params_t *params, double 
                  int32_t *launches) {
   if (!plan || !params) { set_error("run: null argument"); return MISOB200_EINVAL; }
   if (int rc = upload(plan->p, *params)) return rc;
-  if (int rc = run_resident(plan->p, nullptr, launches)) return rc;
-  if (int rc = download(plan->p, samples, loglik, assignment, rundata, status)) return rc;
+  // posteriors of finished buckets travel to the host while later buckets run; download()
+  // then only fetches the assignments and counters
+  if (int rc = run_resident(plan->p, nullptr, launches, samples, loglik)) return rc;
+  if (int rc = download(plan->p, nullptr, nullptr, assignment, rundata, status)) return rc;
   run_timing(plan->p, timing_ms);
   return 0;
 }

@@ -78,6 +78,11 @@ struct Plan {
   std::vector<uint8_t> tiles;            // tile arena, each tile 16-byte aligned
   long long n_reads = 0;
   long long n_drawn = 0;
+  // output layout cache (run.cu plan_layout): valid for (lay_chains, lay_S) and lay_genes genes
+  int lay_chains = -1;
+  long long lay_S = -1, lay_n_samples = 0, lay_n_loglik = 0;
+  size_t lay_genes = 0;
+  long long lay_range[2 * (kMaxIso + 1) + 1][4] = {};
   // device side (owned by run.cu)
   void *dev = nullptr;
 };

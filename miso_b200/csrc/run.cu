@@ -63,6 +63,9 @@ struct DevState {
   std::vector<int> items[kBuckets];
   int item_off[kBuckets + 1] = {};
   long long n_samples = 0, n_loglik = 0;
+  long long range[kBuckets + 1][4] = {};   // output ranges per bucket (plan_layout)
+  cudaStream_t cstream = nullptr;          // device->host copies of finished buckets
+  cudaEvent_t cdone = nullptr;
   bool uploaded = false, have_run = false;
   bool pinned_tiles = false, pinned_desc = false;
   std::vector<double> h_ptab;       // plan.ptab + the 1.0 of the uniform-code classes
@@ -95,15 +98,60 @@ static int check_params(const misob200_params_t &p) {
   return 0;
 }
 
-void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, long long *n_loglik) {
-  const long long S = S_of(p);
-  long long so = 0, lo = 0;
+// Work lists: per (tile format, K) bucket, genes by falling number of drawing reads.
+static int bucket_of(const GeneDesc &d) {
+  return (d.status == 0 && d.K >= 2 && d.K <= kMaxIso) ? (d.format ? 1 : 0) * (kMaxIso + 1) + d.K : -1;
+}
+void plan_buckets(const Plan &plan, std::vector<int> (&items)[2 * (kMaxIso + 1)]) {
+  for (auto &v : items) v.clear();
   for (size_t g = 0; g < plan.desc.size(); g++) {
+    const int b = bucket_of(plan.desc[g]);
+    if (b >= 0) items[b].push_back((int) g);
+  }
+  for (auto &v : items)
+    std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return plan.desc[a].R2 > plan.desc[b].R2; });
+}
+
+// Output layout.  The posterior samples of a gene are one block [s*C+c][K] (the reference's
+// column-major K x (C*S), miso.c:884-888); the blocks are laid out in the order the buckets
+// run -- dense before class tiles, K = 8 down to 2, work-list order inside a bucket, genes
+// that do not run last -- so that a finished bucket's outputs are one contiguous range and its
+// device->host copy overlaps the buckets still running (run_resident).  Callers locate a gene
+// through misob200_plan_offsets.  `range` (optional): per bucket [begin, end) in f64 elements
+// of samples, then of loglik; entry 2*(kMaxIso+1) is the tail of genes that do not run.
+void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, long long *n_loglik,
+                 long long (*range_out)[4]) {
+  const long long S = S_of(p);
+  long long (*range)[4] = range_out;
+  if (plan.lay_chains == p.n_chains && plan.lay_S == S && plan.lay_genes == plan.desc.size()) {
+    if (range) std::memcpy(range, plan.lay_range, sizeof(plan.lay_range));
+    *n_samples = plan.lay_n_samples; *n_loglik = plan.lay_n_loglik;
+    return;
+  }
+  range = plan.lay_range;
+  std::vector<int> items[2 * (kMaxIso + 1)];
+  plan_buckets(plan, items);
+  long long so = 0, lo = 0;
+  auto place = [&](int g) {
     plan.desc[g].sample_off = so;
     plan.desc[g].loglik_off = lo;
     so += (long long) plan.desc[g].K * p.n_chains * S;
     lo += (long long) p.n_chains * S;
-  }
+  };
+  for (int fmt = 0; fmt < 2; fmt++)
+    for (int k = kMaxIso; k >= 0; k--) {
+      const int b = fmt * (kMaxIso + 1) + k;
+      const long long s0 = so, l0 = lo;
+      for (int g : items[b]) place(g);
+      range[b][0] = s0; range[b][1] = so; range[b][2] = l0; range[b][3] = lo;
+    }
+  const long long s0 = so, l0 = lo;
+  for (size_t g = 0; g < plan.desc.size(); g++)
+    if (bucket_of(plan.desc[g]) < 0) place((int) g);
+  range[2 * (kMaxIso + 1)][0] = s0; range[2 * (kMaxIso + 1)][1] = so; range[2 * (kMaxIso + 1)][2] = l0; range[2 * (kMaxIso + 1)][3] = lo;
+  plan.lay_chains = p.n_chains; plan.lay_S = S; plan.lay_genes = plan.desc.size();
+  plan.lay_n_samples = so; plan.lay_n_loglik = lo;
+  if (range_out) std::memcpy(range_out, plan.lay_range, sizeof(plan.lay_range));
   *n_samples = so; *n_loglik = lo;
 }
 
@@ -121,6 +169,8 @@ static void free_dev(DevState *st) {
   if (!st->h_drawn.empty()) { cudaHostUnregister(st->h_drawn.data()); cudaGetLastError(); }
   for (auto &s : st->kstream) if (s) cudaStreamDestroy(s);
   if (st->stream) cudaStreamDestroy(st->stream);
+  if (st->cstream) cudaStreamDestroy(st->cstream);
+  if (st->cdone) cudaEventDestroy(st->cdone);
   delete st;
 }
 
@@ -196,6 +246,7 @@ int upload(Plan &plan, const misob200_params_t &p) {
     DevState *old = static_cast<DevState *>(plan.dev);
     if (std::memcmp(&old->params, &p, sizeof(p)) == 0) {
       CK(cudaSetDevice(old->device));
+      plan_layout(plan, p, &old->n_samples, &old->n_loglik, old->range);      // (offsets may have been queried for other parameters)
       return copy_inputs(plan, old);
     }
   }
@@ -210,6 +261,8 @@ int upload(Plan &plan, const misob200_params_t &p) {
   CK(cudaGetDeviceProperties(&prop, p.device));
   st->sm_count = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&st->cstream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&st->cdone, cudaEventDisableTiming));
   for (auto &e : st->ev) CK(cudaEventCreate(&e));
   for (int b = 0; b < kBuckets; b++) {
     if (b % (kMaxIso + 1) < 2) continue;
@@ -219,22 +272,15 @@ int upload(Plan &plan, const misob200_params_t &p) {
     CK(cudaEventCreate(&st->kend[b]));
   }
 
-  plan_layout(plan, p, &st->n_samples, &st->n_loglik);
+  plan_layout(plan, p, &st->n_samples, &st->n_loglik, st->range);
   const size_t G = plan.desc.size();
 
   // work lists: per (tile format, K), genes ordered by decreasing number of drawing reads
   int total = 0;
-  for (int b = 0; b < kBuckets; b++) st->items[b].clear();
-  for (size_t g = 0; g < G; g++) {
-    const GeneDesc &d = plan.desc[g];
-    if (d.status == 0 && d.K >= 2 && d.K <= kMaxIso) st->items[(d.format ? 1 : 0) * (kMaxIso + 1) + d.K].push_back((int) g);
-  }
+  plan_buckets(plan, st->items);
   for (int b = 0; b < kBuckets; b++) {
-    auto &v = st->items[b];
-    std::stable_sort(v.begin(), v.end(),
-                     [&](int a, int b) { return plan.desc[a].R2 > plan.desc[b].R2; });
     st->item_off[b] = total;
-    total += (int) v.size();
+    total += (int) st->items[b].size();
   }
   st->item_off[kBuckets] = total;
 
@@ -476,7 +522,7 @@ static int launch_k(Plan &plan, DevState *st, int k, int *nl) {
   return 0;
 }
 
-int run_resident(Plan &plan, double *kernel_ms, int *launches) {
+int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples, double *h_loglik) {
   DevState *st = static_cast<DevState *>(plan.dev);
   if (!st || !st->uploaded) { set_error("run_resident: plan is not on the device (call misob200_upload)"); return MISOB200_EINVAL; }
   CK(cudaSetDevice(st->device));
@@ -542,10 +588,35 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches) {
       if (rc) return rc;
       CK(cudaEventRecord(st->kend[b], st->kstream[b]));
       CK(cudaEventRecord(st->kdone[b], st->kstream[b]));
+      // a finished bucket's posteriors are one contiguous range (plan_layout): copy them out
+      // while the later buckets run
+      if (h_samples || h_loglik) {
+        CK(cudaStreamWaitEvent(st->cstream, st->kdone[b], 0));
+        const long long *r = st->range[b];
+        if (h_samples && r[1] > r[0])
+          CK(cudaMemcpyAsync(h_samples + r[0], st->d_samples + r[0], (r[1] - r[0]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
+        if (h_loglik && r[3] > r[2])
+          CK(cudaMemcpyAsync(h_loglik + r[2], st->d_loglik + r[2], (r[3] - r[2]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
+      }
       if (serial || st->last_n_seg > 1 || st->last_fill >= 0.6) prev = b;
       CK(cudaStreamWaitEvent(st->stream, st->kdone[b], 0));
     }
   CK(cudaEventRecord(st->ev[3], st->stream));
+  if (h_samples || h_loglik) {
+    // genes that did not run (status != 0): their zeroed blocks, the tail of the layout; and
+    // buckets skipped by a development switch
+    for (int b = 0; b <= kBuckets; b++) {
+      const bool ran = b < kBuckets && !st->items[b].empty() && !(only_k && b % (kMaxIso + 1) != only_k);
+      if (ran) continue;
+      const long long *r = st->range[b];
+      CK(cudaStreamWaitEvent(st->cstream, st->ev[2], 0));
+      if (h_samples && r[1] > r[0])
+        CK(cudaMemcpyAsync(h_samples + r[0], st->d_samples + r[0], (r[1] - r[0]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
+      if (h_loglik && r[3] > r[2])
+        CK(cudaMemcpyAsync(h_loglik + r[2], st->d_loglik + r[2], (r[3] - r[2]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
+    }
+    CK(cudaStreamSynchronize(st->cstream));
+  }
   CK(cudaStreamSynchronize(st->stream));
   CK(cudaGetLastError());
 #ifdef MISOB200_SEG_DEBUG
@@ -632,7 +703,7 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
 // numpy's (the module does `from numpy import *`), i.e. half-to-even on the
 // fp64 product; the host computes the two indices with the same expression --
 // plus the per-isoform assigned-read counts of chain 0.
-__global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, int S, int lo, int hi,
+__global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, int S, int lo, int hi, int n_pad,
                                const double *samples, const uint8_t *drawn, const int *accrej,
                                double *summary) {
   extern __shared__ double vals[];
@@ -675,18 +746,22 @@ __global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, 
       }
       __syncthreads();
       mean = s_red[0];
-      // rank selection: element with exactly `lo` (`hi`) elements before it
-      // in the stable order (value, index)
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double v = vals[i];
-        int rank = 0;
-        for (int j = 0; j < n; j++) {
-          const double w = vals[j];
-          rank += (w < v) || (w == v && j < i);
+      // order statistics: bitonic sort of the n values (padded with +inf to a power of two)
+      // in shared memory, then elements lo and hi (Python indexing: -1 wraps)
+      for (int i = n + threadIdx.x; i < n_pad; i += blockDim.x) vals[i] = INFINITY;
+      __syncthreads();
+      for (int kk = 2; kk <= n_pad; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+          for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+            const int p = i ^ j;
+            if (p > i) {
+              const double a = vals[i], b = vals[p];
+              if ((a > b) == ((i & kk) == 0)) { vals[i] = b; vals[p] = a; }
+            }
+          }
+          __syncthreads();
         }
-        if (rank == (lo < 0 ? n + lo : lo)) s_red[1] = v;      // Python index -1 wraps
-        if (rank == (hi < 0 ? n + hi : hi)) s_red[2] = v;
-      }
+      if (threadIdx.x == 0) { s_red[1] = vals[lo < 0 ? n + lo : lo]; s_red[2] = vals[hi < 0 ? n + hi : hi]; }
       __syncthreads();
       vlo = s_red[1]; vhi = s_red[2];
       __syncthreads();
@@ -713,12 +788,14 @@ int summarize(Plan &plan, double *summary) {
   const int G = (int) plan.desc.size();
   if (G == 0) return 0;
   const int S = S_of(st->params), n = st->params.n_chains * S;
-  const size_t smem = std::max(n, 1) * sizeof(double);
+  int n_pad = 1;
+  while (n_pad < n) n_pad <<= 1;
+  const size_t smem = (size_t) n_pad * sizeof(double);
   if (smem > 200 * 1024) { set_error("summarize: too many samples per gene for the on-chip selection"); return MISOB200_UNIMPLEMENTED; }
   CK(cudaFuncSetAttribute(summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const double alpha = 1 - 0.95;
   const int lo = (int) nearbyint((alpha / 2) * n) - 1, hi = (int) nearbyint((1 - alpha / 2) * n) - 1;
-  summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, S, lo, hi, st->d_samples,
+  summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, S, lo, hi, n_pad, st->d_samples,
                                               st->d_drawn, st->d_accrej, st->d_summary);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(summary, st->d_summary, (size_t) G * MISOB200_SUMMARY_F64 * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
