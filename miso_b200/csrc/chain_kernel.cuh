@@ -167,15 +167,22 @@ template <int K>
 __device__ __forceinline__ Derived derive(double alpha, double offset_k, double hyper_m1_k,
                                           double lg_sum, double lg_each, int gb, int mi) {
   constexpr int len = K - 1;
+  // The K-wide serial sums below are unrolled for K <= 6 only: at K = 8 the unrolled 64-bit
+  // shuffles of this function alone were ~3 KB of code, and the per-iteration instruction
+  // footprint of the K = 7, 8 kernels sat right at the 32 KB instruction cache (ncu: "no
+  // instruction" was the largest stall, 2-3 cycles per issue).  Rolled loops keep the
+  // reference's summation order and cost a few more dynamic instructions: K = 8 192 -> 179 ms,
+  // K = 7 159 -> 154 ms, but K = 6 130 -> 136 ms (profiles/r1_ab14_rolled_shuffles.log).
+  constexpr int U = K <= 6 ? K : 1;
   Derived r;
   const double e = d_exp(alpha);
   double sumexp = 0.0;
-#pragma unroll
+#pragma unroll (U)
   for (int i = 0; i < len; i++) sumexp = sumexp + shfl_d(e, gb + i);
   sumexp = sumexp + 1.0;
   double psi = d_div(e, sumexp);
   double sumpsi = 0.0;
-#pragma unroll
+#pragma unroll (U)
   for (int i = 0; i < len; i++) sumpsi = sumpsi + shfl_d(psi, gb + i);
   if (mi == len) psi = 1 - sumpsi;
   r.psi = psi;
@@ -183,28 +190,28 @@ __device__ __forceinline__ Derived derive(double alpha, double offset_k, double 
   const double lg = d_log(psi);
   const double t = lg + offset_k;
   double mx = shfl_d(t, gb);
-#pragma unroll
+#pragma unroll (U)
   for (int i = 1; i < K; i++) {
     const double v = shfl_d(t, gb + i);
     if (v > mx) mx = v;
   }
   const double ex = d_exp(t - mx);
   double sum = 0.0;
-#pragma unroll
+#pragma unroll (U)
   for (int i = 0; i < K; i++) sum = sum + shfl_d(ex, gb + i);
   sum = d_log(sum) + mx;
   r.lp = t - sum;
 
   const double term = hyper_m1_k * lg;
   double dir = 0.0;
-#pragma unroll
+#pragma unroll (U)
   for (int i = 0; i < K; i++) dir = dir + shfl_d(term, gb + i);
   dir = dir + lg_sum;
   dir = dir - lg_each;
   r.dir = dir;
 
   double lth = 1.0, prod = 1.0;
-#pragma unroll
+#pragma unroll (U)
   for (int i = 0; i < len; i++) {
     const double at = shfl_d(psi, gb + i);
     lth = lth - at;
@@ -218,12 +225,20 @@ __device__ __forceinline__ Derived derive(double alpha, double offset_k, double 
 // sum_k n_k * v_k in isoform order within the lane's group, skipping isoforms nothing
 // is assigned to
 template <int K>
-__device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb) {
+__device__ __forceinline__ double count_dot_body(int cnt_k, double v_k, int gb) {
   const double a = cnt_k ? (double) cnt_k * v_k : 0.0;
   double s = 0.0;
-#pragma unroll
+#pragma unroll (K <= 6 ? K : 1)
   for (int i = 0; i < K; i++) s = s + shfl_d(a, gb + i);
   return s;
+}
+template <int K>
+__device__ __noinline__ double count_dot_shared(int cnt_k, double v_k, int gb) { return count_dot_body<K>(cnt_k, v_k, gb); }
+// (K >= 7: one shared body for the three calls of an iteration, see derive)
+template <int K>
+__device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb) {
+  if (K >= 7) return count_dot_shared<K>(cnt_k, v_k, gb);
+  return count_dot_body<K>(cnt_k, v_k, gb);
 }
 
 template <int K, bool SMEM, bool WIDE, int FMT>
@@ -380,7 +395,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     const double t2 = nwB.q - alpha;                         // theta = psiNew, mu = alpha
     const double e1 = d_div((-0.5) * t1 * t1, sigma), e2 = d_div((-0.5) * t2 * t2, sigma);
     double ep1 = 0.0, ep2 = 0.0;
-#pragma unroll
+#pragma unroll (K <= 6 ? K - 1 : 1)
     for (int i = 0; i < len; i++) { ep1 = ep1 + shfl_d(e1, gb + i); ep2 = ep2 + shfl_d(e2, gb + i); }
     const double xe = d_exp(mi == 0 ? ep1 : ep2);
     const double pdf = covar * (mi == 0 ? cur.prod : nwB.prod) * xe;

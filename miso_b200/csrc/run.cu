@@ -354,12 +354,15 @@ static void set_segments(ChainParams &P, DevState *st, int b, long long n_units,
   P.ring_tail = st->d_ring_tail + b;
 }
 
+#ifndef MISOB200_WARPS
+#define MISOB200_WARPS 4      /* warps per CTA of chain_kernel (A/B builds: 6 with MISOB200_MINBLOCKS_CLASS=3) */
+#endif
 template <int K, int FMT>
 static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   const int b = FMT * (kMaxIso + 1) + K;
   const auto &v = st->items[b];
   if (v.empty()) return 0;
-  constexpr int WARPS = 4;
+  constexpr int WARPS = MISOB200_WARPS;
   // per-warp shared memory: the largest tile of the bucket (+ threshold rows, class format)
   int slot = 0, cls = 0, thr = 0;
   for (int g : v) {
