@@ -162,6 +162,10 @@ struct Derived {
   double prod;     // group-uniform   : 1 / prod(theta) / ltheta (miso.c:110)
 };
 
+#ifndef MISOB200_ROLL_FROM_K
+#define MISOB200_ROLL_FROM_K 7      /* K-wide shuffle sums are rolled loops from this K on (see derive) */
+#endif
+constexpr int kRollFromK = MISOB200_ROLL_FROM_K;
 // gb = first lane of this lane's group, mi = member index (lane - gb)
 template <int K>
 __device__ __forceinline__ Derived derive(double alpha, double offset_k, double hyper_m1_k,
@@ -173,7 +177,7 @@ __device__ __forceinline__ Derived derive(double alpha, double offset_k, double 
   // instruction" was the largest stall, 2-3 cycles per issue).  Rolled loops keep the
   // reference's summation order and cost a few more dynamic instructions: K = 8 192 -> 179 ms,
   // K = 7 159 -> 154 ms, but K = 6 130 -> 136 ms (profiles/r1_ab14_rolled_shuffles.log).
-  constexpr int U = K <= 6 ? K : 1;
+  constexpr int U = K < kRollFromK ? K : 1;
   Derived r;
   const double e = d_exp(alpha);
   double sumexp = 0.0;
@@ -228,7 +232,7 @@ template <int K>
 __device__ __forceinline__ double count_dot_body(int cnt_k, double v_k, int gb) {
   const double a = cnt_k ? (double) cnt_k * v_k : 0.0;
   double s = 0.0;
-#pragma unroll (K <= 6 ? K : 1)
+#pragma unroll (K < kRollFromK ? K : 1)
   for (int i = 0; i < K; i++) s = s + shfl_d(a, gb + i);
   return s;
 }
@@ -237,7 +241,7 @@ __device__ __noinline__ double count_dot_shared(int cnt_k, double v_k, int gb) {
 // (K >= 7: one shared body for the three calls of an iteration, see derive)
 template <int K>
 __device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb) {
-  if (K >= 7) return count_dot_shared<K>(cnt_k, v_k, gb);
+  if (K >= kRollFromK) return count_dot_shared<K>(cnt_k, v_k, gb);
   return count_dot_body<K>(cnt_k, v_k, gb);
 }
 
@@ -395,7 +399,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
     const double t2 = nwB.q - alpha;                         // theta = psiNew, mu = alpha
     const double e1 = d_div((-0.5) * t1 * t1, sigma), e2 = d_div((-0.5) * t2 * t2, sigma);
     double ep1 = 0.0, ep2 = 0.0;
-#pragma unroll (K <= 6 ? K - 1 : 1)
+#pragma unroll (K < kRollFromK ? K - 1 : 1)
     for (int i = 0; i < len; i++) { ep1 = ep1 + shfl_d(e1, gb + i); ep2 = ep2 + shfl_d(e2, gb + i); }
     const double xe = d_exp(mi == 0 ? ep1 : ep2);
     const double pdf = covar * (mi == 0 ? cur.prod : nwB.prod) * xe;

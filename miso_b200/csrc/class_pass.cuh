@@ -40,7 +40,16 @@ constexpr double kThrMargin = 0x1p-15;
 #ifndef MISOB200_UNROLL_SCORE
 #define MISOB200_UNROLL_SCORE 1
 #endif
+#ifndef MISOB200_UNROLL1_FROM_K
+#define MISOB200_UNROLL1_FROM_K 5
+#endif
 constexpr int kUnrollCount = MISOB200_UNROLL_COUNT, kUnrollScore = MISOB200_UNROLL_SCORE;
+// The counting loop is unrolled by two only for K <= 4.  From K = 5 on, one Philox block per trip:
+// the unrolled body (~370 instructions at K = 8) plus the per-iteration scalar code no longer fit
+// the instruction caches (6 KB L0, 32 KB L1.5) and the fetch stalls cost more than the second
+// block's ILP brings: K = 8 181 -> 167 ms, K = 7 152 -> 145, K = 6 130 -> 122, K = 5 105 -> 104,
+// K = 4 unchanged (profiles/README.md, r1_ab17).
+constexpr int kUnroll1FromK = MISOB200_UNROLL1_FROM_K;
 
 // Threshold rows live in two planes so that a row never spans more than 16 bytes: plane A
 // holds t_0..t_3 of every class (stride TSA <= 16), plane B t_4..t_6 (stride TSB, K >= 6).
@@ -190,7 +199,7 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
   const uint32_t ncls = (uint32_t) cr.ncls;
   double rp_lane = 0.0;
   uint32_t tot = 0;                                   // MODE 1: sum of the G_k so far
-#pragma unroll (MODE == 0 ? kUnrollCount : kUnrollScore)
+#pragma unroll (MODE == 0 ? (K >= kUnroll1FromK ? 1 : kUnrollCount) : kUnrollScore)
   for (int s = 0; s < nsteps; s++) {
     uint32_t x[4];
     philox4x32_10(Q0 + (uint32_t) (lane + 32 * s), 0u, gene, chain, key, x);
