@@ -392,7 +392,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(args.workload, G), "peak_source": how,
                          "algorithmic_bytes_per_step": alg,
-                         "kernel": "chain_kernel<K,4>, K=2..8 (7 concurrent launches per step)",
+                         "kernel": "chain_kernel<K> / quad_kernel<K>, one launch per isoform-count bucket K = 2..8 (7 launches per step)",
                          "bucket_ms_per_step": {str(k): bucket[k] / args.steps for k in range(2, 9) if bucket[k] > 0}},
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "setup_seconds": {"synthetic_generation": t_gen, "host_plan_stage": t_plan},

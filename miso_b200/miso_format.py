@@ -120,6 +120,13 @@ def format_credible_intervals(event_name, samples, confidence_level=0.95):
     return [event_name, "%.2f" % s.mean(axis=0)[0], "%.2f" % ci[0], "%.2f" % ci[1]]
 
 
+def isoforms_field(header):
+    """``get_isoforms_from_header`` (``samples_utils.py:177-189``): the isoforms= value without
+    its brackets."""
+    v = header.get("isoforms", "")
+    return v[1:-1] if v.startswith("[") and v.endswith("]") else v
+
+
 # ---- two-sample comparison (compare_miso) -----------------------------------------
 
 BF_HEADER = ["event_name", "sample1_posterior_mean", "sample1_ci_low", "sample1_ci_high",
@@ -162,7 +169,7 @@ def format_bf_line(event_name, samples1, samples2, bf, header1, header2):
         diff = ",".join("%.2f" % v for v in (m1 - m2))
         bfs = ",".join("%.2f" % max(v, 0) for v in bf)
     return "\t".join([event_name, mean1, c1[2], c1[3], mean2, c2[2], c2[3], diff, bfs,
-                      header1.get("isoforms", ""), header1.get("counts", ""),
+                      isoforms_field(header1), header1.get("counts", ""),
                       header1.get("assigned_counts", ""), header2.get("counts", ""),
                       header2.get("assigned_counts", ""), header1.get("chrom", "NA"),
                       header1.get("strand", "NA"), header1.get("mRNA_starts", ""),

@@ -1,6 +1,8 @@
 """`.miso` writer / parser / credible intervals (miso_b200/miso_format.py) --
 the on-disk contract of misopy/miso_sampler.py:376-466 and
 misopy/credible_intervals.py:4-55."""
+import os
+
 import numpy as np
 
 from miso_b200 import miso_format as mf
@@ -78,3 +80,38 @@ def test_bayes_factor_matches_scipy_kde():
     assert mf.bayes_factor(a, b)[0] == 1e12
     line = mf.format_bf_line("ev", s1[:, :2], s2[:, :2], got, {"isoforms": "['a','b']"}, {})
     assert line.count("\t") == len(mf.BF_HEADER) - 1
+
+
+def test_summarize_and_compare_directories(tmp_path):
+    """summarize_miso / compare_miso over sample directories (samples_utils.py:263-329,
+    hypothesis_test.py:182-345)."""
+    from miso_b200 import postprocess as pp
+    rng = np.random.default_rng(5)
+    for label, shift in (("ctrl", 0.0), ("kd", 0.5)):
+        for ev, K in (("evA", 2), ("evB", 3)):
+            psi = rng.dirichlet(np.ones(K) * 200, size=300)
+            psi[:, 0] = np.clip(psi[:, 0] + shift, 0, 1)
+            psi /= psi.sum(axis=1, keepdims=True)
+            header = mf.format_header([["a%d" % k] for k in range(K)], [("a%d" % k, 100) for k in range(K)], 3500, 500,
+                                      10, 40.0, "drift", tuple((1.0,) * K for _ in range(1)), (300.0,),
+                                      np.zeros(300, int), "chr1", "+", [10] * K, [900] * K)
+            d = tmp_path / label / "chr1"
+            d.mkdir(parents=True, exist_ok=True)
+            mf.write_miso(str(d / (ev + ".miso")), header, psi, np.zeros(300))
+    (tmp_path / "kd" / "chr1" / "evC.miso").write_text((tmp_path / "kd" / "chr1" / "evA.miso").read_text())
+    n = pp.summarize_sampler_results(str(tmp_path / "ctrl"), str(tmp_path / "out" / "ctrl.miso_summary"))
+    assert n == 2
+    lines = (tmp_path / "out" / "ctrl.miso_summary").read_text().splitlines()
+    assert lines[0].split("\t") == pp.SUMMARY_HEADER
+    fa = lines[1].split("\t")
+    assert fa[0] == "evA" and fa[4] == "'a0','a1'" and fa[7:9] == ["chr1", "+"]
+    smp = mf.load_samples(str(tmp_path / "ctrl" / "chr1" / "evA.miso"))[0]
+    assert fa[1] == "%.2f" % smp.mean(axis=0)[0]
+    assert len(lines[2].split("\t")[1].split(",")) == 3              # multi-isoform: comma-separated means
+    path, m = pp.output_samples_comparison(str(tmp_path / "ctrl"), str(tmp_path / "kd"), str(tmp_path / "cmp"))
+    assert m == 2 and path.endswith(os.path.join("ctrl_vs_kd", "bayes-factors", "ctrl_vs_kd.miso_bf"))
+    rows = [ln.split("\t") for ln in open(path).read().splitlines()]
+    assert rows[0] == mf.BF_HEADER and [r[0] for r in rows[1:]] == ["evA", "evB"]
+    s2 = mf.load_samples(str(tmp_path / "kd" / "chr1" / "evA.miso"))[0]
+    assert float(rows[1][8]) == float("%.2f" % mf.bayes_factor(smp, s2)[0]) and float(rows[1][8]) > 100
+    assert abs(float(rows[1][7]) - (smp.mean(axis=0)[0] - s2.mean(axis=0)[0])) < 0.011
