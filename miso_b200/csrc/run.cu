@@ -449,7 +449,10 @@ static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
     for (int g : v) r2 += plan.desc[g].R2;
     const char *lim = std::getenv("MISOB200_QUAD_MAX_READS");
     const char *cpw = std::getenv("MISOB200_CHAINS_PER_WARP");      // "4": tests force the layout
-    const long long max_mean = lim ? std::atoll(lim) : (cpw && std::atoi(cpw) == 4) ? (1LL << 40) : 1200;
+    // (K = 2 has the cheapest counting pass -- one threshold per read -- so the scalar part weighs
+    // more at a given read count: cfg-2, 750 drawing reads, runs 1.6x faster four to a warp; at
+    // K = 3 and ~1000 reads the two layouts are level once the single layout is cut into segments)
+    const long long max_mean = lim ? std::atoll(lim) : (cpw && std::atoi(cpw) == 4) ? (1LL << 40) : (K == 2 ? 1200 : 850);
     if (!v.empty() && r2 > max_mean * (long long) v.size()) return 0;
   }
   const int slot = ((core + 127) & ~127) + 32;     // 32 mod 128: the four groups' id words fall in different banks
