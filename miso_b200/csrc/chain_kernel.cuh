@@ -261,6 +261,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   const double sigma = d.sigma, sd = d.sd, covar = d.covar_const;
   const int R2 = d.R2, row_bytes = d.row_bytes, flag_off = d.flag_off, paired = d.paired;
   const int ucode_off = d.ucode_off;
+  const bool lp_safe = d.lp_safe != 0 && d.lp_max < P.n_neglog;
   int g_always[K];
 #pragma unroll
   for (int k = 0; k < K; k++) g_always[k] = FMT == 1 ? d.g_always[k] : 0;
@@ -359,7 +360,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
       } else if (ok) {
         // (only paired-end passes get here with a read score to compute; see rec_next)
         class_pass_rp<K, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gid, (uint32_t) chain, key, g_always,
-                                     P.neglog, P.n_neglog, &c, &rp_drawn);
+                                     P.neglog, P.n_neglog, lp_safe, &c, &rp_drawn);
       } else {     // final pass of chain 0, thresholds declined, or weights that underflow
         class_literal<K, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, cur.psi, n_u, R2, gid, (uint32_t) chain, key, paired, L,
                                      P.neglog, P.n_neglog, &c, &rp_drawn, last ? ass_out : nullptr);

@@ -170,7 +170,7 @@ __device__ __forceinline__ double neg_log_lp(int lp, const double *__restrict__ 
 // draw is conditional, miso.c:870, so a pass starts at an arbitrary phase).  The id
 // row carries 3 null ids in front and null ids behind: phantom ranks count nothing.
 //   MODE 0: counts only.
-//   MODE 1: + the read score of the chosen isoforms (paired-end, miso_paired.c:157-163);
+//   MODE 1, 2: + the read score of the chosen isoforms (paired-end, miso_paired.c:157-163);
 //           runs before an iteration that records a sample (the MH ratio does not need
 //           the read score, the recorded log score does).
 template <int K, int MODE, bool SMEM, bool WIDE>
@@ -206,7 +206,7 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
     const uint32_t ids = __byte_perm(TM::ld(a), TM::ld(a + 4), sel);
     a += 128;
     uint32_t uc01 = 0, uc23 = 0;                      // MODE 1: the 4 reads' own codes
-    if (MODE == 1) {
+    if (MODE >= 1) {
       if (!WIDE) {
         uc01 = __byte_perm(TM::ld(ua), TM::ld(ua + 4), sel);
       } else {
@@ -225,7 +225,7 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
 #pragma unroll
       for (int k = 0; k < NT; k++)      // G_k += (w > t_k): carry out of w + ~t_k, added with carry
         asm("{\n\t.reg .u32 j;\n\tadd.cc.u32 j, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(G[k]) : "r"(x[i]), "r"(nt[k]));
-      if (MODE == 1) {
+      if (MODE >= 1) {
         uint32_t now = 0;
 #pragma unroll
         for (int k = 0; k < NT; k++) now += G[k];
@@ -237,7 +237,10 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
         else cc = __byte_perm(i < 2 ? uc01 : uc23, 0u, (i & 1) ? 0x4432u : 0x4410u);
         if (!(meta & 0x100u)) cc = lds_u16(cr.rec_s + 16u * id + 2u * chosen);   // not a uniform-code class
         const int lp = (int) lds_u32(cr.l_s + 4u * chosen) - ((int) cc - 1);
-        const double sc = neg_log_lp(lp, neglog, n_neglog) + lds_f64(ptab_s + cc * 8u);   // isoscores, miso_paired.c:409-411
+        // isoscores, miso_paired.c:409-411; MODE 2: the host checked that every lp this gene can
+        // produce is inside the table (GeneDesc.lp_safe), no range test and no log() call in the loop
+        const double nl = MODE == 2 ? __ldg(neglog + lp) : neg_log_lp(lp, neglog, n_neglog);
+        const double sc = nl + lds_f64(ptab_s + cc * 8u);
         if (id != ncls) rp_lane += sc;
       }
     }
@@ -248,7 +251,7 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
 #pragma unroll
   for (int k = 1; k < NT; k++) cnt[k] = (int) (G[k - 1] - G[k]);
   cnt[K - 1] = (int) G[NT - 1];
-  if (MODE == 1) {
+  if (MODE >= 1) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) rp_lane += __shfl_xor_sync(0xffffffffu, rp_lane, d);
     rp = rp_lane;
@@ -268,10 +271,15 @@ template <int K, bool SMEM, bool WIDE>
 __device__ __noinline__ void class_pass_rp(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
                                            uint32_t ptab_s, unsigned long long n_u, int R2, uint32_t gene,
                                            uint32_t chain, const PhiloxKey &key, const int *__restrict__ g_always,
-                                           const double *__restrict__ neglog, int n_neglog, int *cnt_k, double *rp) {
+                                           const double *__restrict__ neglog, int n_neglog, bool lp_safe, int *cnt_k,
+                                           double *rp) {
   int cnt[K];
-  class_pass_body<K, 1, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gene, chain, key, g_always, neglog, n_neglog,
-                                    cnt, *rp);
+  if (lp_safe)
+    class_pass_body<K, 2, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gene, chain, key, g_always, neglog, n_neglog,
+                                      cnt, *rp);
+  else
+    class_pass_body<K, 1, SMEM, WIDE>(rows, ucode_off, cr, ptab_s, n_u, R2, gene, chain, key, g_always, neglog, n_neglog,
+                                      cnt, *rp);
   const int lane = threadIdx.x & 31;
   int c = 0;
 #pragma unroll

@@ -213,6 +213,15 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
       d.offset[k] = std::log(acc);
     }
   }
+  if (paired) {
+    // the read-score passes look -log(lp) up in a table, lp = L_k - (code - 1), code in [1, n_codes):
+    // if every such lp is >= 1 the kernel can skip the range test (class_pass.cuh MODE 2)
+    int lo = d.L[0], hi = d.L[0];
+    for (int k = 0; k < K; k++) { lo = std::min(lo, d.L[k]); hi = std::max(hi, d.L[k]); }
+    d.lp_min = lo - (n_codes - 2);
+    d.lp_max = hi;
+    d.lp_safe = (d.lp_min >= 1 && !std::getenv("MISOB200_NO_LP_SAFE")) ? 1 : 0;      // (switch: A/B runs)
+  }
   auto read_score = [&](int k, int code) -> double {
     if (!paired) return d.rs_se[k];
     const double lp = d.L[k] - (code - 1);

@@ -43,12 +43,13 @@ struct GeneDesc {
   int flag_off;                  // byte offset of the flag row (always u8) inside the tile
   int tile_bytes;                // whole tile, multiple of 16
   int core_bytes;                // class format: id row + class records (what quad_kernel.cuh keeps in shared memory)
-  int pad_[1];
+  int lp_safe;                   // paired-end: every lp = L_k - (code - 1) a drawing read can produce lies in [lp_min, lp_max], lp_min >= 1
   // ---- class format (format == 1, class_kernel.cuh) -------------------------
   int format;                    // 0: dense code rows + flag row; 1: class ids + uniform codes + class records
   int ncls;                      // weight classes among the drawing reads (<= kMaxClasses)
   int cls_off;                   // byte offset of the class records (ncls x 8 u16 ptab indices, then ncls + 1 u32 meta)
   int ucode_off;                 // byte offset of the uniform-code row (u8, or u16 when the plan is "wide")
+  int lp_min, lp_max, pad2_[2];  // see lp_safe
   int g_always[kMaxIso];         // drawing reads whose first compatible isoform comes after k (their test k
                                  // is true whatever the uniform: the cumulative sum is still an exact 0)
 };

@@ -206,3 +206,35 @@ def test_degenerate_genes_in_one_batch(mb, port, chains_per_warp):
         assert_gene_parity(r, want, tag="degenerate case %d" % i)
     assert (plan.gene_result(out, 1)["assignment"] == -1).all()
     assert (plan.gene_result(out, 4)["assignment"] == -1).all()
+
+
+def test_read_score_lookup_checked_and_unchecked(mb, port, monkeypatch):
+    """The read-score passes look -log(lp) up in a table; genes whose lp range the host proved
+    inside the table skip the range test (GeneDesc.lp_safe, class_pass.cuh MODE 2).  (a) isoforms
+    shorter than the longest insert length: lp can leave the table, the checked path must run;
+    (b) an ordinary batch forced through the checked path."""
+    rng = np.random.default_rng(9)
+    exons = ((1, 100), (201, 260), (401, 500))
+    isoforms = ((0, 1, 2), (0, 2))
+    genes, poss, cigs, raw = [], [], [], []
+    for g in range(12):
+        psi = rng.dirichlet(np.ones(2))
+        pos, cig = simulate_pairs(exons, isoforms, psi, 400, 36, 150.0, 20.0, 4.0, rng)
+        genes.append(mb.Gene(exons, isoforms)); poss.append(pos); cigs.append(cig)
+        raw.append((exons, isoforms, pos, cig))
+    rb = mb.ReadBatch(genes, poss, cigs, 36, 1, True, 150.0, 400.0, 4.0)
+    plan = mb.Plan().append(rb)
+    fp, fs = plan.fragment_table()
+    assert fs + len(fp) - 1 > 200          # inserts longer than the short isoform exist in the model
+    params = mb.make_params(n_iters=400, burn_in=50, lag=5, n_chains=2, seed=31)
+    out = plan.run(params)
+    for g, wl_gene in enumerate(raw):
+        want = oracle_gene(port, wl_gene, True, params, gene_id=g, pe=(150.0, 400.0, 4.0))
+        assert_gene_parity(plan.gene_result(out, g), want, tag="short isoform gene %d" % g)
+    monkeypatch.setenv("MISOB200_NO_LP_SAFE", "1")
+    w = mb.Workload(1, 16, 400, 36, 250.0, 900.0, 4.0, seed=12)
+    plan = mb.Plan().append(w)
+    out = plan.run(params)
+    for g in range(16):
+        want = oracle_gene(port, w.gene(g), True, params, gene_id=g)
+        assert_gene_parity(plan.gene_result(out, g), want, tag="checked lookup gene %d" % g)
