@@ -315,19 +315,41 @@ def compute_gene_psi(gene_ids, gff_filename, sam_filename, output_dir, read_len,
 
 def main(argv=None):
     import argparse
-    ap = argparse.ArgumentParser(description="MISO PSI sampler on the B200: GFF3 + SAM -> .miso files")
-    ap.add_argument("--compute-gene-psi", nargs=4, metavar=("GENE_IDS", "GFF", "SAM", "OUTPUT_DIR"), required=True,
+    ap = argparse.ArgumentParser(
+        description="MISO on the B200: GFF3 + SAM -> .miso files (miso --run), .miso_summary "
+                    "(summarize_miso --summarize-samples), .miso_bf (compare_miso --compare-samples)")
+    ap.add_argument("--compute-gene-psi", nargs=4, metavar=("GENE_IDS", "GFF", "SAM", "OUTPUT_DIR"),
                     help="comma-separated gene ids (or 'all'), GFF3 annotation, SAM alignments, output directory")
-    ap.add_argument("--read-len", type=int, required=True)
+    ap.add_argument("--summarize-samples", nargs=2, metavar=("SAMPLES_DIR", "OUTPUT_DIR"),
+                    help="write OUTPUT_DIR/summary/<name of SAMPLES_DIR>.miso_summary (summarize_miso.py:24-47)")
+    ap.add_argument("--compare-samples", nargs=3, metavar=("SAMPLES_DIR_1", "SAMPLES_DIR_2", "OUTPUT_DIR"),
+                    help="Bayes factors of every event both samples have (compare_miso.py:40-95)")
+    ap.add_argument("--read-len", type=int)
     ap.add_argument("--overhang-len", type=int, default=1)
     ap.add_argument("--paired-end", nargs=2, type=float, metavar=("MEAN", "SD"), default=None)
     ap.add_argument("--seed", type=int, default=None)
     a = ap.parse_args(argv)
-    ids, gff, sam, out = a.compute_gene_psi
-    gene_ids = list(load_gff_genes(gff)) if ids == "all" else ids.split(",")
-    res = compute_gene_psi(gene_ids, gff, sam, out, a.read_len, a.overhang_len, a.paired_end, seed=a.seed, verbose=True)
-    for gid, r in res.items():
-        print("%s\t%s" % (gid, r))
+    if a.summarize_samples:
+        from .postprocess import summarize_sampler_results
+        samples_dir, out = a.summarize_samples
+        name = os.path.basename(os.path.normpath(samples_dir))
+        path = os.path.join(out, "summary", "%s.miso_summary" % name)
+        print("%s\t%d events" % (path, summarize_sampler_results(samples_dir, path)))
+    elif a.compare_samples:
+        from .postprocess import output_samples_comparison
+        path, n = output_samples_comparison(*a.compare_samples)
+        print("%s\t%d events" % (path, n))
+    elif a.compute_gene_psi:
+        if a.read_len is None:
+            ap.error("--compute-gene-psi needs --read-len")
+        ids, gff, sam, out = a.compute_gene_psi
+        gene_ids = list(load_gff_genes(gff)) if ids == "all" else ids.split(",")
+        res = compute_gene_psi(gene_ids, gff, sam, out, a.read_len, a.overhang_len, a.paired_end, seed=a.seed,
+                               verbose=True)
+        for gid, r in res.items():
+            print("%s\t%s" % (gid, r))
+    else:
+        ap.error("one of --compute-gene-psi, --summarize-samples, --compare-samples is required")
 
 
 if __name__ == "__main__":

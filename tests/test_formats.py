@@ -115,3 +115,20 @@ def test_summarize_and_compare_directories(tmp_path):
     s2 = mf.load_samples(str(tmp_path / "kd" / "chr1" / "evA.miso"))[0]
     assert float(rows[1][8]) == float("%.2f" % mf.bayes_factor(smp, s2)[0]) and float(rows[1][8]) > 100
     assert abs(float(rows[1][7]) - (smp.mean(axis=0)[0] - s2.mean(axis=0)[0])) < 0.011
+
+
+def test_cli_summarize_and_compare(tmp_path, capsys):
+    from miso_b200 import run_miso
+    rng = np.random.default_rng(2)
+    for label in ("s1", "s2"):
+        psi = rng.dirichlet(np.ones(2) * 50, size=100)
+        header = mf.format_header([["a"], ["b"]], [("a", 10), ("b", 20)], 1500, 500, 10, 50.0, "drift", ((1.0, 1.0),),
+                                  (100.0,), np.zeros(100, int), "chr2", "-", [1, 1], [9, 9])
+        d = tmp_path / label / "chr2"
+        d.mkdir(parents=True)
+        mf.write_miso(str(d / "ev.miso"), header, psi, np.zeros(100))
+    run_miso.main(["--summarize-samples", str(tmp_path / "s1"), str(tmp_path / "out")])
+    assert (tmp_path / "out" / "summary" / "s1.miso_summary").read_text().count("\n") == 2
+    run_miso.main(["--compare-samples", str(tmp_path / "s1"), str(tmp_path / "s2"), str(tmp_path / "out")])
+    assert (tmp_path / "out" / "s1_vs_s2" / "bayes-factors" / "s1_vs_s2.miso_bf").is_file()
+    assert "1 events" in capsys.readouterr().out
