@@ -121,7 +121,8 @@ int match_on_device(const misob200_reads_t &in, const MatchParams &mp, int devic
   out.codes_store.assign((size_t) std::max<long long>(n_codes, 1), 0);
   out.codes = out.codes_store.data();
 
-  void *d[10] = {nullptr};
+  // device buffers: 0-8 inputs (order of `src`), 9 codes, 10 per-gene status + the work counter
+  void *d[11] = {nullptr};
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   auto cleanup = [&]() {
@@ -132,28 +133,16 @@ int match_on_device(const misob200_reads_t &in, const MatchParams &mp, int devic
   MCK(cudaSetDevice(device));
   MCK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   for (auto &e : ev) MCK(cudaEventCreate(&e));
-  const size_t sz[10] = {
+  const size_t sz[11] = {
       (size_t) (G + 1) * 4, (size_t) (n_iso + 1) * 4, (size_t) std::max(n_exon, 1) * 4, (size_t) std::max(n_exon, 1) * 4,
       (size_t) (G + 1) * 8, (size_t) std::max<long long>(n_reads, 1) * 4, (size_t) (n_reads + 1) * 8,
-      (size_t) std::max<long long>(n_cig, 1), (size_t) (G + 1) * 8, (size_t) std::max<long long>(n_codes, 1) * 2};
+      (size_t) std::max<long long>(n_cig, 1), (size_t) (G + 1) * 8, (size_t) std::max<long long>(n_codes, 1) * 2,
+      (size_t) G * 4 + 4};
   const void *src[9] = {in.iso_off, in.exon_off, in.exon_start, in.exon_end, in.read_off, in.position, in.cigar_off,
                         in.cigar, out.code_off.data()};
-  for (int i = 0; i < 10; i++) MCK(cudaMalloc(&d[i], sz[i]));
-  int *d_status = nullptr;
-  unsigned *d_next = nullptr;
-  MCK(cudaMalloc(&d_status, (size_t) G * 4 + 4));
-  d_next = reinterpret_cast<unsigned *>(d_status + G);
-  auto cleanup2 = [&]() { cudaFree(d_status); cleanup(); };
-#undef MCK
-#define MCK(call)                                                                          \
-  do {                                                                                     \
-    cudaError_t e_ = (call);                                                               \
-    if (e_ != cudaSuccess) {                                                               \
-      set_error(std::string("match_on_device: ") + cudaGetErrorString(e_));                \
-      cleanup2();                                                                          \
-      return MISOB200_ECUDA;                                                               \
-    }                                                                                      \
-  } while (0)
+  for (int i = 0; i < 11; i++) MCK(cudaMalloc(&d[i], sz[i]));
+  int *d_status = static_cast<int *>(d[10]);
+  unsigned *d_next = reinterpret_cast<unsigned *>(d_status + G);
   MCK(cudaMemsetAsync(d_status, 0, (size_t) G * 4 + 4, stream));
   MCK(cudaEventRecord(ev[0], stream));
   long long bytes_in = 0;
@@ -193,7 +182,7 @@ int match_on_device(const misob200_reads_t &in, const MatchParams &mp, int devic
   out.bytes_out = n_codes * 2;
   t_kernel_ms = out.kernel_ms; t_h2d_ms = out.h2d_ms; t_d2h_ms = out.d2h_ms;
   t_bytes_in = out.bytes_in; t_bytes_out = out.bytes_out;
-  cleanup2();
+  cleanup();
   return 0;
 }
 
