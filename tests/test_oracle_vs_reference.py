@@ -85,3 +85,25 @@ def test_start_random_port_equals_reference(ref, port, t):
     rc = (port.miso_se(ex, iso, pos, cig, rl, 300, 50, 5, **kw) if t % 2 == 0 else
           port.miso_pe(ex, iso, pos, cig, rl, 250.0, 900.0, 4.0, 300, 50, 5, **kw))
     assert not np.array_equal(rb["samples"], rc["samples"])
+
+
+@pytest.mark.parametrize("t", range(6))
+def test_port_equals_reference_with_hyperparameters_and_uniform_start(ref, port, t):
+    """Non-flat Dirichlet hyperparameters (ldirichlet, src/miso.c:165-182, enters the MH ratio) and
+    MISO_START_UNIFORM (src/miso.c:372-386): port and unmodified reference bit for bit."""
+    rng = np.random.default_rng(9000 + t)
+    K = int(rng.integers(2, 9))
+    ex, iso = _gene(rng, K, t % 2)
+    psi = rng.dirichlet(np.ones(K))
+    hyper = tuple(float(h) for h in rng.uniform(0.3, 3.0, K))
+    R, rl, C = int(rng.integers(30, 250)), 36, int(rng.integers(1, 3))
+    kw = dict(overhang=int(rng.integers(1, 4)), chains=C, seed=50 + t, gene_id=t, start=t % 2, hyper=hyper)
+    if t % 3 == 0:
+        pos, cig, _ = ref.simulate_se(ex, iso, psi, R, rl, seed=t)
+        ra, rb = ref.miso_se(ex, iso, pos, cig, rl, 250, 50, 4, **kw), port.miso_se(ex, iso, pos, cig, rl, 250, 50, 4, **kw)
+    else:
+        pos, cig, _ = ref.simulate_pe(ex, iso, psi, R, rl, 200.0, 625.0, 4.0, seed=t)
+        ra = ref.miso_pe(ex, iso, pos, cig, rl, 200.0, 625.0, 4.0, 250, 50, 4, **kw)
+        rb = port.miso_pe(ex, iso, pos, cig, rl, 200.0, 625.0, 4.0, 250, 50, 4, **kw)
+    for k in ra:
+        np.testing.assert_array_equal(ra[k], rb[k], err_msg=k)
