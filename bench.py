@@ -5,21 +5,27 @@ Metric (BASELINE.json): gene-chain iterations/sec at 1/2/4/8 B200 vs the
 reference pysplicing C path on host CPU.  A "step" is one pass of the hot path
 over one batch: the cfg-3 workload of BASELINE.json configs[2] -- 50k mixed
 events (2-8 isoforms), 2k paired-end reads each with the insert-length model,
-5000 iterations (burn-in 500, lag 10, 1 chain) -- generated synthetically inside
-the library (miso_b200/csrc/synth.cpp).  With N > 1 every rank owns a full-size
-shard of its own (weak scaling; genes are independent, no data-path collective)
-and the per-gene posterior summaries are all-gathered once per step over NCCL.
+5000 iterations (burn-in 500, lag 10, 1 chain), synthetic (workloads/synth.cpp).
+
+N > 1 (BASELINE cfg-4): THE SAME 50k-event workload is dealt to the N ranks
+(longest-processing-time first, miso_b200/shard.py), every rank plans and runs
+only its shard -- no data-path collective -- and the step ends with one NCCL
+all-gather of the 256-byte per-gene posterior summaries, device to device
+("scaling": "strong").  `--scaling weak` gives every rank a full-size shard of
+its own instead (secondary number).  `--workload cfg5`: two samples of the 50k
+events (both on the rank that owns the event) + Bayes factors on the device,
+all-gather of the comparison records.
 
   value : whole-job iterations/s with the packed tiles already resident in HBM
           (misob200_run_resident), CUDA-event time, max over ranks
   e2e   : the same metric through the public C entry point misob200_run with
           host buffers: pinned tiles H2D + kernels + D2H of posteriors + the
-          host epilogue, every step, plus the summary all-gather
-  roofline / cpu_baseline / clocks: see DESIGN.md "measurement"
+          host epilogue, every step, plus summary kernel and all-gather
+  roofline / cpu_baseline / clocks / parity_checked: see DESIGN.md "measurement"
 
 `--impl reference` times the reference's own CPU implementation (oracle/_ref,
 the unmodified C core; falls back to the plain-C port) on all host cores on a
-bounded sample of the same workload.
+bounded sample of the same workload, a different slice every step.
 """
 import argparse
 import json
@@ -36,15 +42,21 @@ METRIC = "gene-chain iterations/sec"
 UNIT = "iterations/s"
 
 WORKLOADS = {
-    # name: (kind, n_genes, reads_per_gene, paired)
-    "cfg3": dict(kind=1, n_genes=50000, reads=2000, label="cfg-3: 50k mixed events (K 2-8), 2k PE reads each, "
-                 "insert N(250,30^2) +-4sd, read_len 36"),
-    "cfg2": dict(kind=0, n_genes=10000, reads=1000, label="cfg-2: 10k 2-isoform SE events, 1k SE reads each, read_len 36"),
+    # name: kind (0 SE K=2, 1 PE mixed K), events, reads per event, samples per event
+    "cfg3": dict(kind=1, n_genes=50000, reads=2000, samples=1,
+                 label="cfg-3: 50k mixed events (K 2-8), 2k PE reads each, insert N(250,30^2) +-4sd, read_len 36"),
+    "cfg2": dict(kind=0, n_genes=10000, reads=1000, samples=1,
+                 label="cfg-2: 10k 2-isoform SE events, 1k SE reads each, read_len 36"),
+    "cfg5": dict(kind=1, n_genes=50000, reads=2000, samples=2,
+                 label="cfg-5: two samples of the 50k mixed events of cfg-3 (different psi) + Bayes-factor comparison"),
 }
 ITERS, BURN, LAG, CHAINS = 5000, 500, 10, 1
 PE = (250.0, 900.0, 4.0)
 READ_LEN = 36
 SEED = 20260925
+# relative cost of one gene-chain per isoform count (measured bucket times per gene on a B200,
+# BENCH_r01: 24 / 71 / 92 / 100 / 118 / 138 / 160 ms per ~7.1k genes), times reads: the LPT key
+COST_PER_READ = {2: 24, 3: 71, 4: 92, 5: 100, 6: 118, 7: 138, 8: 160}
 
 
 def algorithmic_bytes(info, S):
@@ -127,25 +139,31 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU arm (reference implementation on host cores)
+# CPU arm (reference implementation on host cores).  Imports workloads/ and oracle/
+# only: nothing of libmiso_b200.so is mapped by these processes.
 
-def _cpu_worker(args):
-    """One process: run the oracle on a slice of genes, return (iterations, seconds)."""
-    kind_ref, genes, paired, mt = args
+_ORACLE = None
+
+
+def _cpu_init(kind_ref):
+    global _ORACLE
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refdriver
-    orc = refdriver.RefOracle() if kind_ref == "reference" else refdriver.PortOracle()
+    _ORACLE = refdriver.RefOracle() if kind_ref == "reference" else refdriver.PortOracle()
+
+
+def _cpu_gene(args):
+    """One gene through the oracle; returns (iterations, seconds)."""
+    gene, gid, paired = args
+    ex, isos, pos, cig = gene
+    kw = dict(iters=ITERS, burn=BURN, lag=LAG, chains=CHAINS, seed=SEED, gene_id=gid,
+              rng_mode=1 if _ORACLE.kind == "reference" else 0)      # reference: its own MT19937 (fastest)
     t0 = time.perf_counter()
-    n = 0
-    for (ex, isos, pos, cig, gid) in genes:
-        kw = dict(iters=ITERS, burn=BURN, lag=LAG, chains=CHAINS, seed=SEED, gene_id=gid,
-                  rng_mode=1 if (mt and kind_ref == "reference") else 0)
-        if paired:
-            orc.miso_pe(ex, isos, pos, cig, READ_LEN, PE[0], PE[1], PE[2], **kw)
-        else:
-            orc.miso_se(ex, isos, pos, cig, READ_LEN, **kw)
-        n += ITERS * CHAINS
-    return n, time.perf_counter() - t0
+    if paired:
+        _ORACLE.miso_pe(ex, isos, pos, cig, READ_LEN, PE[0], PE[1], PE[2], **kw)
+    else:
+        _ORACLE.miso_se(ex, isos, pos, cig, READ_LEN, **kw)
+    return ITERS * CHAINS, time.perf_counter() - t0
 
 
 def usable_cores():
@@ -162,61 +180,145 @@ def usable_cores():
     return n
 
 
-def cpu_arm(wl, genes_per_core, cores=None):
-    """Reference C path on `cores` processes over the first genes of the workload."""
-    import concurrent.futures as cf
-    import multiprocessing as mp
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import refdriver
-    import miso_b200 as mb
-    kind_ref = "reference" if refdriver.available() else "port"
-    if kind_ref == "port" and not refdriver.port_available():
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
-    cores = cores or usable_cores()
-    n = cores * genes_per_core
-    w = mb.Workload(wl["kind"], n, wl["reads"], READ_LEN, PE[0], PE[1], PE[2], seed=SEED, first_gene_id=0)
-    slices = [[] for _ in range(cores)]
-    for g in range(n):
-        ex, isos, pos, cig = w.gene(g)
-        slices[g % cores].append((ex, isos, pos, cig, g))
-    w.close()
-    paired = wl["kind"] == 1
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with cf.ProcessPoolExecutor(max_workers=cores, mp_context=ctx) as ex:
-        res = list(ex.map(_cpu_worker, [(kind_ref, s, paired, True) for s in slices]))
-    wall = time.perf_counter() - t0
-    busy = max(r[1] for r in res)
-    iters = sum(r[0] for r in res)
-    return dict(value=iters / busy, unit=UNIT, cores=cores, kind=kind_ref,
-                sample="%d genes of the workload (%d per core), %d iterations each, %d worker processes = all "
-                       "usable host cores (%d logical CPUs visible, cgroup quota applied) in parallel, %s; busy "
-                       "%.1fs wall %.1fs" % (
-                           n, genes_per_core, ITERS, cores, os.cpu_count() or 0,
-                           "reference's own MT19937 stream" if kind_ref == "reference" else "Philox stream",
-                           busy, wall),
-                seconds=busy)
+class CpuArm:
+    """Reference C path on all usable host cores: a persistent pool of worker processes
+    that pull genes one at a time (longest first), so a step's time is not the imbalance of
+    a static split.  value = iterations / wall time of the step."""
+
+    def __init__(self, wl):
+        import multiprocessing as mp
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import refdriver
+        self.kind = "reference" if refdriver.available() else "port"
+        if self.kind == "port" and not refdriver.port_available():
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
+        self.wl = wl
+        self.cores = usable_cores()
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(self.kind,))
+        self.pool.map(_noop, range(self.cores * 4))          # workers up, library loaded
+
+    def step(self, first_gene, n):
+        """genes first_gene .. first_gene + n - 1 of the workload"""
+        from workloads import Workload
+        wl = self.wl
+        w = Workload(wl["kind"], n, wl["reads"], READ_LEN, PE[0], PE[1], PE[2], seed=SEED, first_gene_id=first_gene)
+        K = w.n_iso()
+        order = sorted(range(n), key=lambda g: -int(K[g]))
+        jobs = [(w.gene(g), first_gene + g, wl["kind"] == 1) for g in order]
+        w.close()
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_gene, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        return dict(iters=sum(r[0] for r in res), wall=wall, busy=sum(r[1] for r in res), genes=n)
+
+    def describe(self, steps):
+        genes = sum(s["genes"] for s in steps)
+        wall = sum(s["wall"] for s in steps)
+        busy = sum(s["busy"] for s in steps)
+        return ("%d genes of the workload (%.1f%% of its %d events; a different slice of %d genes every step), %d "
+                "iterations each; %d persistent worker processes = all usable host cores (%d logical CPUs visible, "
+                "cgroup quota applied) pulling one gene at a time, longest first; %s; wall %.1fs, summed worker "
+                "time %.1fs (pool efficiency %.2f)" % (
+                    genes, 100.0 * genes / self.wl["n_genes"], self.wl["n_genes"], steps[0]["genes"], ITERS,
+                    self.cores, os.cpu_count() or 0,
+                    "reference's own MT19937 stream" if self.kind == "reference" else "Philox stream",
+                    wall, busy, busy / (wall * self.cores)))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def _noop(_):
+    return 0
+
+
+def cpu_baseline_leg(wl, genes_per_core):
+    arm = CpuArm(wl)
+    s = arm.step(0, arm.cores * genes_per_core)
+    out = dict(value=s["iters"] / s["wall"], unit=UNIT, cores=arm.cores, kind=arm.kind, sample=arm.describe([s]))
+    arm.close()
+    return out
 
 
 # ---------------------------------------------------------------------------
 
-def build_plan(mb, wl, n_genes, first_gene_id, chunk=5000):
+def shard_ids(wl, rank, world, scaling):
+    """Gene ids of this rank.  strong: the one workload dealt LPT by cost; weak: a private full-size shard."""
+    import numpy as np
+    n = wl["n_genes"]
+    if world == 1:
+        return np.arange(n, dtype=np.uint32), n
+    if scaling == "weak":
+        return np.arange(rank * n, (rank + 1) * n, dtype=np.uint32), n * world
+    from workloads import Workload
+    from miso_b200.shard import shard_genes
+    w = Workload(wl["kind"], n, 0, READ_LEN, PE[0], PE[1], PE[2], seed=SEED)      # structures only
+    K = w.n_iso()
+    w.close()
+    cost = np.array([COST_PER_READ.get(int(k), 160) for k in K], np.int64) * wl["reads"]
+    return shard_genes(cost, world)[rank].astype(np.uint32), n
+
+
+def build_plan(mb, wl, ids, sample=0, chunk=5000, match_device=None):
+    from workloads import Workload
     plan = mb.Plan()
     t_gen = t_plan = 0.0
-    done = 0
-    while done < n_genes:
-        n = min(chunk, n_genes - done)
+    for i in range(0, len(ids), chunk):
         t0 = time.perf_counter()
-        w = mb.Workload(wl["kind"], n, wl["reads"], READ_LEN, PE[0], PE[1], PE[2], seed=SEED,
-                        first_gene_id=first_gene_id + done)
+        w = Workload(wl["kind"], 0, wl["reads"], READ_LEN, PE[0], PE[1], PE[2], seed=SEED,
+                     gene_ids=ids[i:i + chunk], sample=sample)
         t1 = time.perf_counter()
-        plan.append(w)
+        plan.append(w, match_device=match_device)
         t2 = time.perf_counter()
         w.close()
         t_gen += t1 - t0
         t_plan += t2 - t1
-        done += n
     return plan, t_gen, t_plan
+
+
+def parity_leg(mb, wl, plan, out, ids, per_k=2):
+    """Untimed: the unmodified reference (oracle/_ref; else the pinned port), driven by the same
+    Philox stream, on a seeded sample of the very genes that were timed -- `per_k` per isoform
+    count.  Counts bit-exact, posterior mean / 95% CI within 1e-3 (BASELINE.json north_star)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdriver
+    from workloads import Workload
+    oracle = refdriver.RefOracle() if refdriver.available() else refdriver.PortOracle()
+    info = plan.info()
+    rng = np.random.default_rng(SEED)
+    pick = []
+    for k in sorted(set(int(x) for x in info[:, 0])):
+        cand = np.flatnonzero((info[:, 0] == k) & (info[:, 4] == 0))
+        pick += [int(g) for g in rng.choice(cand, size=min(per_k, len(cand)), replace=False)]
+    w = Workload(wl["kind"], 0, wl["reads"], READ_LEN, PE[0], PE[1], PE[2], seed=SEED, gene_ids=ids[pick])
+    worst_mean = worst_ci = 0.0
+    exact = True
+    for j, g in enumerate(pick):
+        ex, isos, pos, cig = w.gene(j)
+        kw = dict(iters=ITERS, burn=BURN, lag=LAG, chains=1, seed=SEED, gene_id=int(ids[g]), rng_mode=0)
+        if wl["kind"] == 1:
+            want = oracle.miso_pe(ex, isos, pos, cig, READ_LEN, PE[0], PE[1], PE[2], **kw)
+        else:
+            want = oracle.miso_se(ex, isos, pos, cig, READ_LEN, **kw)
+        got = plan.gene_result(out, g)
+        S = (ITERS - BURN) // LAG
+        exact = exact and bool((got["assignment"] == want["assignment"]).all()) \
+            and int(got["rundata"][5]) == int(want["rundata"][5]) and int(got["rundata"][6]) == int(want["rundata"][6])
+        a, b = got["samples"][:, :S], want["samples"][:, :S]
+        worst_mean = max(worst_mean, float(np.abs(a.mean(axis=1) - b.mean(axis=1)).max()))
+        lo, hi = int(np.floor(0.025 * S + 0.5)) - 1, int(np.floor(0.975 * S + 0.5)) - 1
+        sa, sb = np.sort(a, axis=1), np.sort(b, axis=1)
+        worst_ci = max(worst_ci, float(np.abs(sa[:, [lo, hi]] - sb[:, [lo, hi]]).max()))
+    w.close()
+    res = {"genes": len(pick), "oracle": oracle.kind, "counts_bit_exact": exact,
+           "max_abs_mean_diff": worst_mean, "max_abs_ci_diff": worst_ci,
+           "what": "per-read assignments and accept/reject counts equal; posterior mean and 95% CI bounds vs the "
+                   "oracle on the same stream, %d genes per isoform count of the timed plan" % per_k}
+    if not exact or worst_mean > 1e-3 or worst_ci > 1e-3:
+        raise SystemExit("bench.py: PARITY FAILURE on the timed plan: %s" % json.dumps(res))
+    return res
 
 
 _JSON_OUT = None
@@ -245,9 +347,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--genes", type=int, default=0, help="override events per GPU (debugging only)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the one workload sharded over the ranks (cfg-4), weak = one full-size shard per rank")
+    ap.add_argument("--genes", type=int, default=0, help="override the number of events (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-genes-per-core", type=int, default=40)
+    ap.add_argument("--ref-genes-per-core-per-step", type=int, default=10)
+    ap.add_argument("--match-device", action="store_true", help="plan stage: read<->isoform matching on the GPU")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -257,43 +364,50 @@ def main():
     if args.genes:
         wl["n_genes"] = args.genes
     S = (ITERS - BURN) // LAG
-    config = {"workload": wl["label"] + "; %d iterations, burn-in %d, lag %d, %d chain; %d events per GPU"
-              % (ITERS, BURN, LAG, CHAINS, wl["n_genes"]),
-              "events_per_gpu": wl["n_genes"], "reads_per_event": wl["reads"],
-              "parallelism": "genes sharded over %d GPU(s), one process per GPU" % world,
-              "l2_note": "packed inputs (hundreds of MB) exceed the 126 MB L2; no flush needed"}
+    scaling = args.scaling if world > 1 else "strong"
+    total_events = wl["n_genes"] * (world if scaling == "weak" else 1)
+    config = {"workload": wl["label"] + "; %d iterations, burn-in %d, lag %d, %d chain; %d events in total"
+              % (ITERS, BURN, LAG, CHAINS, total_events),
+              "events_total": total_events, "reads_per_event": wl["reads"], "samples_per_event": wl["samples"],
+              "parallelism": ("1 GPU" if world == 1 else
+                              "dp%d: the workload's events dealt LPT to %d ranks, one process per GPU, one NCCL "
+                              "all-gather of the summaries per step" % (world, world) if scaling == "strong" else
+                              "dp%d: one full-size shard per rank (weak scaling), one NCCL all-gather per step" % world),
+              "l2_note": "packed inputs (tens to hundreds of MB per GPU) are read once per step and the outputs "
+                         "(>= 140 MB per GPU) exceed the 126 MB L2; no flush needed"}
 
     # ------------------------------------------------------------------ CPU arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        per_step = max(1, args.cpu_genes_per_core // 8)
-        vals = []
-        base = None
+        arm = CpuArm(wl)
+        per_step = arm.cores * args.ref_genes_per_core_per_step
+        steps = []
         for i in range(args.warmup + args.steps):
-            base = cpu_arm(wl, per_step)
+            s = arm.step((i * per_step) % max(wl["n_genes"] - per_step, 1), per_step)
             if i >= args.warmup:
-                vals.append(base)
-        v = sum(b["value"] for b in vals) / len(vals)
-        ms = 1e3 * sum(b["seconds"] for b in vals) / len(vals)
+                steps.append(s)
+        v = sum(s["iters"] for s in steps) / sum(s["wall"] for s in steps)
+        ms = 1e3 * sum(s["wall"] for s in steps) / len(steps)
+        sample = arm.describe(steps)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": base["cores"], "kind": base["kind"],
-                                 "sample": base["sample"]},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        arm.close()
         emit(line)
         return 0
 
     # ------------------------------------------------------------------ GPU arm
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_arm(wl, args.cpu_genes_per_core)      # before CUDA is touched in this process
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_leg(wl, args.cpu_genes_per_core)      # before CUDA is touched in this process
 
     import numpy as np
     import miso_b200 as mb
-    from miso_b200._lib import lib, check, ptr
+    from miso_b200._lib import lib, check, ptr, pinned_empty
     import ctypes as C
 
     if mb.device_count() < 1:
@@ -301,8 +415,9 @@ def main():
     device = local_rank % mb.device_count()
 
     if world > 1:
+        import datetime
         import torch.distributed as dist     # rendezvous only (unique-id broadcast); no tensors
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(minutes=30))
         check(lib.misob200_init(device))
         idbuf = (C.c_char * 128)()
         if rank == 0:
@@ -318,27 +433,60 @@ def main():
         check(lib.misob200_comm_barrier_max(ptr(v)))
         return float(v[0])
 
-    plan, t_gen, t_plan = build_plan(mb, wl, wl["n_genes"], first_gene_id=rank * wl["n_genes"])
+    def barrier_sum_i64(x):
+        if world == 1:
+            return int(x)
+        t = [None] * world
+        dist.all_gather_object(t, int(x))
+        return int(sum(t))
+
+    ids, _ = shard_ids(wl, rank, world, scaling)
+    md = device if args.match_device else None
+    plans, t_gen, t_plan = [], 0.0, 0.0
+    for smp in range(wl["samples"]):
+        p, tg, tp = build_plan(mb, wl, ids, sample=smp, match_device=md)
+        plans.append(p)
+        t_gen += tg
+        t_plan += tp
     params = mb.make_params(ITERS, BURN, LAG, CHAINS, seed=SEED, device=device)
-    info = plan.info()
+    info = plans[0].info()
     G = info.shape[0]
-    ok = int((info[:, 4] == 0).sum())
-    iters_per_step = ok * CHAINS * ITERS
-    out = plan.alloc_outputs(params, pinned=True)
-    summ_all = np.zeros((world * G, 32)) if world > 1 else None
+    ok = sum(int((p.info()[:, 4] == 0).sum()) for p in plans)
+    iters_local = ok * CHAINS * ITERS
+    iters_total = barrier_sum_i64(iters_local)
+    n_pad = int(barrier_max(float(G)))
+    outs = [p.alloc_outputs(params, pinned=True) for p in plans]
+    gathered = pinned_empty(world * n_pad * 32, np.float64) if world > 1 else None
+    extra_launches = 0
 
     def e2e_step():
-        plan.run(params, out)
-        s = plan.summarize()
+        nl = 0
+        for p, o in zip(plans, outs):
+            p.run(params, o)
+            nl += o["launches"]
+        if wl["samples"] == 2:
+            if world > 1:
+                check(lib.misob200_comm_allgather_compare(plans[0].h, plans[1].h, n_pad, ptr(gathered)))
+            else:
+                plans[0].compare(plans[1])
+            return nl + 1
         if world > 1:
-            check(lib.misob200_comm_allgather(ptr(s), s.size, ptr(summ_all)))
-        return out["launches"]
+            check(lib.misob200_comm_allgather_summaries(plans[0].h, n_pad, ptr(gathered)))
+        else:
+            plans[0].summarize()
+        return nl + 1
 
     def resident_step():
-        return plan.run_resident()
+        ms = nl = 0
+        for p in plans:
+            a, b = p.run_resident()
+            ms += a
+            nl += b
+        return ms, nl
 
     # warm-up: both paths
-    plan.upload(params)
+    for p in plans:
+        p.upload(params)
     for _ in range(args.warmup):
         resident_step()
     clocks = ClockSampler(device)
@@ -350,7 +498,8 @@ def main():
         ms, nl = resident_step()
         dev_ms += ms
         launches += nl
-        bucket += plan.bucket_timing()
+        for p in plans:
+            bucket += p.bucket_timing()
     wall_res = time.perf_counter() - t0
     clk = clocks.stop()
     dev_ms = barrier_max(dev_ms)
@@ -361,40 +510,63 @@ def main():
         e2e_step()
     barrier_max(0.0)
     t0 = time.perf_counter()
+    e2e_launches = 0
     for _ in range(args.steps):
-        e2e_step()
+        e2e_launches += e2e_step()
     wall_e2e = barrier_max(time.perf_counter() - t0)
-    h2d, d2h = plan.transfer_bytes()
-    timing = out["timing_ms"].copy()
+    h2d = d2h = 0
+    for p in plans:
+        a, b = p.transfer_bytes()
+        h2d += a
+        d2h += b
+    if world > 1:
+        d2h += gathered.nbytes
+    timing = outs[0]["timing_ms"].copy()
+    e2e_ms = 1e3 * wall_e2e / args.steps
 
-    # sanity of what was computed (not timed): posterior means vs simulation truth on a few genes
-    r0 = plan.gene_result(out, 0)
-    assert r0["status"] == 0 and np.isfinite(r0["samples"]).all()
+    # what was timed, checked (untimed): the reference on a seeded sample of this very plan
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_leg(mb, wl, plans[0], outs[0], ids)
+    if world > 1 and wl["samples"] == 1:
+        # the gathered table holds every rank's records: all events accounted for
+        tab = np.asarray(gathered).reshape(world, n_pad, 32)
+        status = tab[:, :, 24:32].copy().view(np.int32)[:, :, 11]
+        assert int((status == 0).sum()) * CHAINS * ITERS == iters_total, "all-gather lost records"
 
     if rank == 0:
-        total_iters = iters_per_step * world
         ms_per_step = dev_ms / args.steps
-        value = total_iters / (ms_per_step / 1e3)
-        e2e_val = total_iters / (wall_e2e / args.steps)
-        alg = algorithmic_bytes(info[info[:, 4] == 0], S)
+        value = iters_total / (ms_per_step / 1e3)
+        e2e_val = iters_total / (wall_e2e / args.steps)
+        alg = algorithmic_bytes(info[info[:, 4] == 0], S) * wl["samples"]
         peak, how = hbm_peak()
         achieved = alg / (ms_per_step / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config,
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * wall_e2e / args.steps,
+                    "ms_per_step": e2e_ms,
                     "last_step_ms": {"h2d": timing[0], "kernels": timing[1], "d2h": timing[2]}},
+            "e2e_with_setup": {"value": iters_total / (e2e_ms / 1e3 + t_plan), "unit": UNIT,
+                               "what": "reads in -> posteriors out: the plan stage (matching, draw order, classes, "
+                                       "tile packing; rank 0's shard, %s) + one e2e step"
+                                       % ("matching on the GPU" if args.match_device else "host threads"),
+                               "plan_stage_s": t_plan, "host_threads": int(lib.misob200_host_threads())},
             "gpu_launches": int(launches),
+            "gpu_launches_e2e": int(e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(args.workload, G), "peak_source": how,
-                         "algorithmic_bytes_per_step": alg,
-                         "kernel": "chain_kernel<K> / quad_kernel<K>, one launch per isoform-count bucket K = 2..8 (7 launches per step)",
+                         "frac": achieved / peak, "traffic": measured_traffic(args.workload, G) if world == 1 else None,
+                         "peak_source": how,
+                         "algorithmic_bytes_per_step": alg, "note": "rank 0's shard; algorithmic bytes and launch "
+                         "time are per rank" if world > 1 else "whole workload",
+                         "kernel": "chain_kernel<K> / quad_kernel<K>, one launch per isoform-count bucket K = 2..8",
                          "bucket_ms_per_step": {str(k): bucket[k] / args.steps for k in range(2, 9) if bucket[k] > 0}},
-            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "cpu_baseline": cpu,
+            "parity_checked": parity,
+            "events_per_s_e2e": total_events / (e2e_ms / 1e3),
             "setup_seconds": {"synthetic_generation": t_gen, "host_plan_stage": t_plan},
             "wall_ms_per_resident_step": 1e3 * wall_res / args.steps,
         }

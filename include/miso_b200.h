@@ -225,32 +225,32 @@ int misob200_compare(misob200_plan_t *plan_a, misob200_plan_t *plan_b, double *o
    the only exchange is one all-gather of the summary records ------------- */
 int misob200_comm_unique_id(char *id128);		/* rank 0 */
 int misob200_comm_init(const char *id128, int n_ranks, int rank);
+/* The path's one collective, device to device: summary kernel on this rank's
+   resident posteriors -> ncclAllGather of the 256-byte records over NVLink ->
+   one device->host copy of the gathered table.  Every rank passes the same
+   n_pad >= its own gene count (all-gather needs equal counts; pad records
+   carry status = -1).  all: n_ranks * n_pad * 32 f64, rank-major. */
+int misob200_comm_allgather_summaries(misob200_plan_t *plan, int64_t n_pad,
+				      double *all);
+/* the same for the two-sample records of misob200_compare (cfg-5) */
+int misob200_comm_allgather_compare(misob200_plan_t *plan_a,
+				    misob200_plan_t *plan_b, int64_t n_pad,
+				    double *all);
+/* generic host-buffer form (tests, small payloads) */
 int misob200_comm_allgather(const double *mine, int64_t n_f64_per_rank,
 			    double *all);
 int misob200_comm_barrier_max(double *value);	/* in: local, out: max */
 int misob200_comm_destroy(void);
 
+/* host worker threads the library uses for the plan stage and the output
+   epilogue: MISOB200_HOST_THREADS, else usable cores (affinity, cgroup quota)
+   divided by LOCAL_WORLD_SIZE */
+int misob200_host_threads(void);
+
 /* page-locked host buffers for the outputs of misob200_run / _download
    (optional: any host pointer works, pinned ones copy at link speed) */
 void *misob200_host_alloc(int64_t bytes);
 int misob200_host_free(void *p);
-
-/* ---- synthetic workloads (BASELINE.json configs 2 and 3) -------------- */
-typedef struct misob200_workload misob200_workload_t;	/* opaque */
-/* kind 0: K=2 skipped-exon SE events (cfg-2); kind 1: K in [2,8] paired-end
-   events with a N(frag_mean, frag_var) insert model (cfg-3).  Genes get ids
-   first_gene_id .. first_gene_id+n_genes-1 and are generated from (seed, id)
-   only, so any shard of a workload can be rebuilt independently. */
-int misob200_workload_create(int kind, int32_t n_genes, int32_t reads_per_gene,
-			     int32_t read_len, double frag_mean,
-			     double frag_var, double num_devs, uint64_t seed,
-			     uint32_t first_gene_id, int n_threads,
-			     misob200_workload_t **out);
-int misob200_workload_view(const misob200_workload_t *w,
-			   misob200_reads_t *view);
-int misob200_workload_truth(const misob200_workload_t *w, int32_t gene,
-			    double *psi);
-int misob200_workload_destroy(misob200_workload_t *w);
 
 #ifdef __cplusplus
 }

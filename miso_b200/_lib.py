@@ -61,8 +61,8 @@ def _load():
     lib.misob200_plan_keep_match.argtypes = [vp, C.c_int]
     lib.misob200_plan_tile_format.argtypes = [vp, C.c_int]
     lib.misob200_plan_gene_tile.argtypes = [vp, C.c_int32, vp, vp, vp]
-    lib.misob200_plan_append.argtypes = [vp, C.POINTER(Reads), C.c_int]
-    lib.misob200_plan_append_device.argtypes = [vp, C.POINTER(Reads), C.c_int, C.c_int]
+    lib.misob200_plan_append.argtypes = [vp, vp, C.c_int]
+    lib.misob200_plan_append_device.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.misob200_last_match_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.misob200_plan_size.argtypes = [vp, vp, vp, vp]
     lib.misob200_plan_gene_info.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
@@ -83,13 +83,9 @@ def _load():
     lib.misob200_comm_unique_id.argtypes = [vp]
     lib.misob200_comm_init.argtypes = [vp, C.c_int, C.c_int]
     lib.misob200_comm_allgather.argtypes = [vp, C.c_int64, vp]
+    lib.misob200_comm_allgather_summaries.argtypes = [vp, C.c_int64, vp]
+    lib.misob200_comm_allgather_compare.argtypes = [vp, vp, C.c_int64, vp]
     lib.misob200_comm_barrier_max.argtypes = [vp]
-    lib.misob200_workload_create.argtypes = [
-        C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
-        C.c_uint64, C.c_uint32, C.c_int, C.POINTER(vp)]
-    lib.misob200_workload_view.argtypes = [vp, C.POINTER(Reads)]
-    lib.misob200_workload_truth.argtypes = [vp, C.c_int32, vp]
-    lib.misob200_workload_destroy.argtypes = [vp]
     return lib
 
 
@@ -106,10 +102,9 @@ EXPORTS = [
     "misob200_run", "misob200_upload", "misob200_run_resident", "misob200_download",
     "misob200_release_device", "misob200_summarize", "misob200_bucket_timing", "misob200_compare",
     "misob200_transfer_bytes", "misob200_comm_unique_id",
-    "misob200_comm_init", "misob200_comm_allgather", "misob200_comm_barrier_max",
+    "misob200_comm_init", "misob200_comm_allgather", "misob200_comm_allgather_summaries",
+    "misob200_comm_allgather_compare", "misob200_host_threads", "misob200_comm_barrier_max",
     "misob200_comm_destroy", "misob200_host_alloc", "misob200_host_free",
-    "misob200_workload_create", "misob200_workload_view", "misob200_workload_truth",
-    "misob200_workload_destroy",
 ]
 
 

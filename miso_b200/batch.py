@@ -101,68 +101,6 @@ class ReadBatch:
         self.struct = r
 
 
-class Workload:
-    """Synthetic inputs generated inside the library (csrc/synth.cpp)."""
-
-    def __init__(self, kind, n_genes, reads_per_gene, read_len=36, frag_mean=250.0,
-                 frag_var=900.0, num_devs=4.0, seed=1, first_gene_id=0, n_threads=0):
-        self.h = C.c_void_p()
-        check(lib.misob200_workload_create(kind, n_genes, reads_per_gene, read_len,
-                                           frag_mean, frag_var, num_devs, seed,
-                                           first_gene_id, n_threads, C.byref(self.h)))
-        self.struct = Reads()
-        check(lib.misob200_workload_view(self.h, C.byref(self.struct)))
-        self.n_genes = n_genes
-
-    def _arr(self, addr, n, dtype):
-        dtype = np.dtype(dtype)
-        buf = (C.c_char * (int(n) * dtype.itemsize)).from_address(addr)
-        return np.frombuffer(buf, dtype=dtype, count=int(n))
-
-    def gene(self, g):
-        """(Gene-like exon lists per isoform, positions, cigars) of gene g, the
-        form the oracle drivers take."""
-        s = self.struct
-        iso_off = self._arr(s.iso_off, s.n_genes + 1, np.int32)
-        n_iso = int(iso_off[-1])
-        exon_off = self._arr(s.exon_off, n_iso + 1, np.int32)
-        n_ex = int(exon_off[-1])
-        xs = self._arr(s.exon_start, n_ex, np.int32)
-        xe = self._arr(s.exon_end, n_ex, np.int32)
-        read_off = self._arr(s.read_off, s.n_genes + 1, np.int64)
-        n_reads = int(read_off[-1])
-        pos = self._arr(s.position, n_reads, np.int32)
-        cig_off = self._arr(s.cigar_off, n_reads + 1, np.int64)
-        blob = self._arr(s.cigar, int(cig_off[-1]), np.uint8)
-        exons, isoforms, seen = [], [], {}
-        for k in range(iso_off[g], iso_off[g + 1]):
-            iso = []
-            for e in range(exon_off[k], exon_off[k + 1]):
-                key = (int(xs[e]), int(xe[e]))
-                if key not in seen:
-                    seen[key] = len(exons)
-                    exons.append(key)
-                iso.append(seen[key])
-            isoforms.append(tuple(iso))
-        r0, r1 = int(read_off[g]), int(read_off[g + 1])
-        raw = blob.tobytes()
-        cig = [raw[cig_off[i]:cig_off[i + 1] - 1].decode() for i in range(r0, r1)]
-        return tuple(exons), tuple(isoforms), pos[r0:r1].copy(), cig
-
-    def truth(self, g, K):
-        out = np.zeros(K)
-        check(lib.misob200_workload_truth(self.h, g, ptr(out)))
-        return out
-
-    def close(self):
-        if self.h:
-            lib.misob200_workload_destroy(self.h)
-            self.h = C.c_void_p()
-
-    def __del__(self):
-        self.close()
-
-
 class Plan:
     def __init__(self, keep_match=False, tile_format=-1):
         """tile_format: -1 class tiles where a gene allows it (default), 0 dense tiles only."""
@@ -177,11 +115,11 @@ class Plan:
     def append(self, reads, n_threads=0, match_device=None):
         """Setup stage for a batch (a-12 ... a-18).  ``match_device``: GPU ordinal that computes
         the read <-> isoform compatibility (csrc/match.cu) instead of the host threads."""
-        struct = reads.struct if hasattr(reads, "struct") else reads
+        struct = reads.struct if hasattr(reads, "struct") else reads      # any misob200_reads_t mirror
         if match_device is None:
-            check(lib.misob200_plan_append(self.h, C.byref(struct), n_threads))
+            check(lib.misob200_plan_append(self.h, C.addressof(struct), n_threads))
         else:
-            check(lib.misob200_plan_append_device(self.h, C.byref(struct), n_threads, int(match_device)))
+            check(lib.misob200_plan_append_device(self.h, C.addressof(struct), n_threads, int(match_device)))
         self._info = None
         return self
 
@@ -330,11 +268,10 @@ class Plan:
         p = out["params"]
         info = self.info()
         K, R = int(info[g, 0]), int(info[g, 1])
-        S = (p.n_iters - p.burn_in) // p.lag
         so, lo, ao = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib.misob200_plan_offsets(self.h, C.byref(p), g, C.addressof(so),
                                         C.addressof(lo), C.addressof(ao)))
-        n = p.n_chains * S
+        n = p.n_chains * (p.n_iters - p.burn_in) // p.lag      # the reference's noSamples (miso.c:661)
         smp = out["samples"][so.value:so.value + K * n].reshape(n, K).T
         return dict(samples=smp, loglik=out["loglik"][lo.value:lo.value + n],
                     assignment=out["assignment"][ao.value:ao.value + R],

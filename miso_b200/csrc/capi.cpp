@@ -26,7 +26,6 @@ int compare(Plan &pa, Plan &pb, double *out);
 
 using namespace misob200;
 
-struct misob200_plan { Plan p; };
 
 extern "C" {
 
@@ -146,7 +145,11 @@ int misob200_plan_fragment_table(const misob200_plan_t *plan, int32_t cap, doubl
 int misob200_plan_offsets(const misob200_plan_t *plan, const misob200_params_t *params, int32_t gene,
                           int64_t *sample_off, int64_t *loglik_off, int64_t *assign_off) {
   if (int rc = check_gene(plan, gene)) return rc;
-  if (!params || params->lag < 1) return MISOB200_EINVAL;
+  if (!params || params->lag < 1 || params->n_iters < 0 || params->burn_in < 0 || params->n_chains < 1 ||
+      params->burn_in > params->n_iters) {
+    set_error("invalid sampler parameters (iterations/burn-in/lag/chains)");
+    return MISOB200_EINVAL;
+  }
   // the layout follows the run order of the buckets (run.cu plan_layout); offsets are derived
   // fields of the descriptors, filled on demand
   Plan &p = const_cast<Plan &>(plan->p);
@@ -162,11 +165,16 @@ int misob200_plan_output_sizes(const misob200_plan_t *plan, const misob200_param
                                int64_t *n_samples_f64, int64_t *n_loglik_f64, int64_t *n_assign_i32) {
   if (!plan || !params || params->lag < 1) return MISOB200_EINVAL;
   const Plan &p = plan->p;
-  const long long S = (params->n_iters - params->burn_in) / params->lag;
+  if (params->n_iters < 0 || params->burn_in < 0 || params->n_chains < 1 || params->burn_in > params->n_iters) {
+    set_error("invalid sampler parameters (iterations/burn-in/lag/chains)");
+    return MISOB200_EINVAL;
+  }
+  // columns per gene block = the reference's noSamples (miso.c:661)
+  const long long cols = (long long) params->n_chains * (params->n_iters - params->burn_in) / params->lag;
   long long so = 0, lo = 0;
   for (size_t g = 0; g < p.desc.size(); g++) {
-    so += (long long) p.desc[g].K * params->n_chains * S;
-    lo += (long long) params->n_chains * S;
+    so += (long long) p.desc[g].K * cols;
+    lo += cols;
   }
   if (n_samples_f64) *n_samples_f64 = so;
   if (n_loglik_f64) *n_loglik_f64 = lo;
@@ -217,6 +225,7 @@ int misob200_compare(misob200_plan_t *plan_a, misob200_plan_t *plan_b, double *o
   if (!plan_a || !plan_b || !out) return MISOB200_EINVAL;
   return compare(plan_a->p, plan_b->p, out);
 }
+int misob200_host_threads(void) { return host_threads(); }
 int misob200_summarize(misob200_plan_t *plan, double *summary) {
   if (!plan || !summary) return MISOB200_EINVAL;
   return summarize(plan->p, summary);

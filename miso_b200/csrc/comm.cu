@@ -7,8 +7,10 @@
 // dlopen so that a single-GPU process never needs it.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 
@@ -36,6 +38,11 @@ ncclComm_t g_comm = nullptr;
 cudaStream_t g_stream = nullptr;
 int g_ranks = 0;
 double *g_scalar = nullptr;
+// persistent, grow-only exchange buffers: one padded record block in, n_ranks blocks out,
+// and a pinned host mirror of the gathered table (nothing is allocated per step)
+double *g_in = nullptr, *g_out = nullptr, *g_host = nullptr;
+size_t g_in_cap = 0, g_out_cap = 0, g_host_cap = 0;
+cudaEvent_t g_ready = nullptr;
 
 int load_nccl() {
   if (N.h) return 0;
@@ -62,7 +69,62 @@ int load_nccl() {
     cudaError_t e_ = (call);                                                       \
     if (e_ != cudaSuccess) { set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); return MISOB200_ECUDA; } \
   } while (0)
+
+int reserve(size_t n_in, size_t n_out) {
+  if (n_in > g_in_cap) {
+    cudaFree(g_in); g_in = nullptr; g_in_cap = 0;
+    CK(cudaMalloc(&g_in, n_in * sizeof(double)));
+    g_in_cap = n_in;
+  }
+  if (n_out > g_out_cap) {
+    cudaFree(g_out); g_out = nullptr; g_out_cap = 0;
+    CK(cudaMalloc(&g_out, n_out * sizeof(double)));
+    g_out_cap = n_out;
+  }
+  if (n_out > g_host_cap) {
+    if (g_host) cudaFreeHost(g_host);
+    g_host = nullptr; g_host_cap = 0;
+    CK(cudaHostAlloc(&g_host, n_out * sizeof(double), cudaHostAllocDefault));
+    g_host_cap = n_out;
+  }
+  return 0;
+}
+
+// records already on this rank's GPU (n of them, rec_f64 doubles each, produced on `producer`)
+// -> every rank's records, rank-major, padded to n_pad records per rank (pad rows: status = -1
+// for the summary layout, zeros otherwise), into `all` (host).
+int allgather_device(const double *d_src, long long n, long long n_pad, int rec_f64, bool summary_layout,
+                     cudaStream_t producer, double *all) {
+  if (!g_comm) { set_error("comm: communicator not initialised (misob200_comm_init)"); return MISOB200_ENCCL; }
+  if (n < 0 || n_pad < n) { set_error("comm: padded record count smaller than the local one"); return MISOB200_EINVAL; }
+  const size_t per = (size_t) std::max<long long>(n_pad, 1) * rec_f64;
+  if (int rc = reserve(per, per * g_ranks)) return rc;
+  CK(cudaEventRecord(g_ready, producer));
+  CK(cudaStreamWaitEvent(g_stream, g_ready, 0));
+  const double *send = d_src;
+  if (n != n_pad || !d_src) {       // unequal shards: pad on the device
+    CK(cudaMemsetAsync(g_in, 0, per * sizeof(double), g_stream));
+    if (n) CK(cudaMemcpyAsync(g_in, d_src, (size_t) n * rec_f64 * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    if (summary_layout && n_pad > n) {
+      // int32 field 11 of the record's integer tail (f64 index 24 + 5, high half) = status -1
+      std::vector<double> tail((size_t) (n_pad - n) * rec_f64, 0.0);
+      for (long long r = 0; r < n_pad - n; r++) reinterpret_cast<int *>(&tail[(size_t) r * rec_f64 + 24])[11] = -1;
+      CK(cudaMemcpyAsync(g_in + (size_t) n * rec_f64, tail.data(), tail.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+      CK(cudaStreamSynchronize(g_stream));     // `tail` is a stack-lifetime pageable source
+    }
+    send = g_in;
+  }
+  NK(N.AllGather(send, g_out, per, ncclFloat64, g_comm, g_stream));
+  CK(cudaMemcpyAsync(g_host, g_out, per * g_ranks * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CK(cudaStreamSynchronize(g_stream));
+  if (all) std::memcpy(all, g_host, per * g_ranks * sizeof(double));
+  return 0;
+}
 }  // namespace
+
+// run.cu
+int summarize_device(Plan &plan, const double **d_summary, cudaStream_t *stream);
+int compare_device(Plan &pa, Plan &pb, const double **d_out, cudaStream_t *stream);
 
 }  // namespace misob200
 
@@ -85,22 +147,42 @@ int misob200_comm_init(const char *id128, int n_ranks, int rank) {
   NK(N.CommInitRank(&g_comm, n_ranks, id, rank));
   CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&g_scalar, 2 * sizeof(double)));
+  CK(cudaEventCreateWithFlags(&g_ready, cudaEventDisableTiming));
   g_ranks = n_ranks;
   return 0;
 }
 
-// mine: n_f64_per_rank doubles in HOST memory (the summaries misob200_summarize
-// returned); all: n_ranks * n_f64_per_rank doubles, rank-major.
+// The path's one collective, device to device: summary kernel on this rank's resident
+// posteriors -> ncclAllGather straight out of the plan's summary buffer (NVLink) -> one
+// device->host copy of the gathered table into pinned memory.  all: n_ranks * n_pad * 32 f64.
+int misob200_comm_allgather_summaries(misob200_plan_t *plan, int64_t n_pad, double *all) {
+  if (!plan) { set_error("comm_allgather_summaries: null plan"); return MISOB200_EINVAL; }
+  const double *d = nullptr;
+  cudaStream_t s = nullptr;
+  if (int rc = summarize_device(plan->p, &d, &s)) return rc;
+  return allgather_device(d, (long long) plan->p.desc.size(), n_pad, MISOB200_SUMMARY_F64, true, s, all);
+}
+
+// cfg-5: Bayes-factor records of this rank's events (both samples resident here) gathered
+// the same way.  all: n_ranks * n_pad * 32 f64.
+int misob200_comm_allgather_compare(misob200_plan_t *plan_a, misob200_plan_t *plan_b, int64_t n_pad, double *all) {
+  if (!plan_a || !plan_b) { set_error("comm_allgather_compare: null plan"); return MISOB200_EINVAL; }
+  const double *d = nullptr;
+  cudaStream_t s = nullptr;
+  if (int rc = compare_device(plan_a->p, plan_b->p, &d, &s)) return rc;
+  return allgather_device(d, (long long) plan_a->p.desc.size(), n_pad, MISOB200_COMPARE_F64, false, s, all);
+}
+
+// mine: n_f64_per_rank doubles in HOST memory; all: n_ranks * n_f64_per_rank doubles,
+// rank-major.  (Generic host-buffer form; the data path uses the device-to-device calls above.)
 int misob200_comm_allgather(const double *mine, int64_t n, double *all) {
   if (!g_comm) { set_error("comm_allgather: communicator not initialised"); return MISOB200_ENCCL; }
-  double *d_in = nullptr, *d_out = nullptr;
-  CK(cudaMalloc(&d_in, std::max<int64_t>(n, 1) * sizeof(double)));
-  CK(cudaMalloc(&d_out, std::max<int64_t>(n, 1) * g_ranks * sizeof(double)));
-  CK(cudaMemcpyAsync(d_in, mine, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-  NK(N.AllGather(d_in, d_out, (size_t) n, ncclFloat64, g_comm, g_stream));
-  CK(cudaMemcpyAsync(all, d_out, n * g_ranks * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  const size_t per = (size_t) std::max<int64_t>(n, 1);
+  if (int rc = reserve(per, per * g_ranks)) return rc;
+  CK(cudaMemcpyAsync(g_in, mine, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+  NK(N.AllGather(g_in, g_out, (size_t) n, ncclFloat64, g_comm, g_stream));
+  CK(cudaMemcpyAsync(all, g_out, n * g_ranks * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
-  cudaFree(d_in); cudaFree(d_out);
   return 0;
 }
 
@@ -117,6 +199,9 @@ int misob200_comm_barrier_max(double *value) {
 int misob200_comm_destroy(void) {
   if (g_comm) { N.CommDestroy(g_comm); g_comm = nullptr; }
   if (g_scalar) { cudaFree(g_scalar); g_scalar = nullptr; }
+  cudaFree(g_in); cudaFree(g_out); g_in = g_out = nullptr; g_in_cap = g_out_cap = 0;
+  if (g_host) { cudaFreeHost(g_host); g_host = nullptr; g_host_cap = 0; }
+  if (g_ready) { cudaEventDestroy(g_ready); g_ready = nullptr; }
   if (g_stream) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   return 0;
 }

@@ -420,23 +420,26 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
     set_error("plan_append: null or negative input"); return MISOB200_EINVAL;
   }
   const int paired = in.paired ? 1 : 0;
+  // validate first; the plan's library fields are only committed by a batch that passes
+  if (in.read_len < 0) { set_error("plan_append: negative read length"); return MISOB200_EINVAL; }
+  if (paired && !(in.frag_var > 0)) { set_error("plan_append: frag_var must be positive"); return MISOB200_EINVAL; }
+  if (paired && !(in.num_devs >= 0)) { set_error("plan_append: num_devs must not be negative"); return MISOB200_EINVAL; }
   if (plan.paired < 0) {
-    plan.paired = paired; plan.read_len = in.read_len; plan.overhang = in.overhang;
+    plan.read_len = in.read_len; plan.overhang = in.overhang;
     plan.frag_mean = in.frag_mean; plan.frag_var = in.frag_var; plan.num_devs = in.num_devs;
     if (paired) {
-      if (!(in.frag_var > 0)) { set_error("plan_append: frag_var must be positive"); return MISOB200_EINVAL; }
       fragment_table(plan);
       plan.wide = plan.ptab.size() > 256;
     } else {
       plan.ptab = {0.0, 1.0}; plan.frag_start = 0; plan.frag_len_n = 1;
     }
+    plan.paired = paired;
   } else if (plan.paired != paired || plan.read_len != in.read_len || plan.overhang != in.overhang ||
              (paired && (plan.frag_mean != in.frag_mean || plan.frag_var != in.frag_var ||
                          plan.num_devs != in.num_devs))) {
     set_error("plan_append: a plan holds one library (read length, overhang, insert model)");
     return MISOB200_EINVAL;
   }
-  if (in.read_len < 0) { set_error("plan_append: negative read length"); return MISOB200_EINVAL; }
 
   const int G = in.n_genes;
   // optional: read <-> isoform compatibility on the GPU
@@ -450,7 +453,7 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
   }
   std::vector<GeneOut> outs(G);
   std::atomic<int> next(0);
-  int nt = n_threads > 0 ? n_threads : (int) std::thread::hardware_concurrency();
+  int nt = n_threads > 0 ? n_threads : host_threads();
   if (nt < 1) nt = 1;
   if (nt > G) nt = G > 0 ? G : 1;
   auto work = [&]() {

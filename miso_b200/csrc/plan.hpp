@@ -106,4 +106,11 @@ void set_error(const std::string &msg);
 // match_device < 0: compatibility on the host; >= 0: on that GPU
 int plan_append(Plan &plan, const misob200_reads_t &reads, int n_threads, int match_device = -1);
 
+// Host worker threads for the plan stage and the output epilogues: MISOB200_HOST_THREADS, else
+// the cores this process may use (affinity mask, cgroup cpu.max quota) divided by the ranks
+// sharing the node (LOCAL_WORLD_SIZE, set by torchrun), at most 32.
+int host_threads();
+
 }  // namespace misob200
+
+struct misob200_plan { misob200::Plan p; };

@@ -13,6 +13,8 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
+
 #include <cuda_runtime.h>
 
 #include "chain_kernel.cuh"
@@ -36,6 +38,30 @@ const char *last_error() { return g_error.c_str(); }
 
 constexpr int kBuckets = 2 * (kMaxIso + 1);
 
+int host_threads() {
+  static int cached = 0;
+  if (cached) return cached;
+  int n = 0;
+  if (const char *e = std::getenv("MISOB200_HOST_THREADS")) n = std::atoi(e);
+  if (n < 1) {
+    n = (int) std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n > 0 ? n : 1 << 20, CPU_COUNT(&set));
+    if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {      // "<quota> <period>" or "max <period>"
+      char q[64];
+      long long period = 0;
+      if (std::fscanf(f, "%63s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0 && period > 0)
+        n = std::min<long long>(n, std::max<long long>(1, (std::atoll(q) + period / 2) / period));
+      std::fclose(f);
+    }
+    int local_world = 1;
+    if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, std::atoi(e));
+    n = std::max(1, n / local_world);
+  }
+  cached = std::max(1, std::min(n, 32));
+  return cached;
+}
+
 struct DevState {
   int device = 0;
   misob200_params_t params{};
@@ -50,6 +76,8 @@ struct DevState {
   double *d_ptab = nullptr, *d_neglog = nullptr;
   int n_neglog = 0;
   double *d_samples = nullptr, *d_loglik = nullptr, *d_summary = nullptr;
+  double *d_compare = nullptr;      // two-sample records (compare_device), grow-only
+  size_t compare_cap = 0;           // ... in events
   uint8_t *d_drawn = nullptr;
   int *d_accrej = nullptr;
   unsigned *d_queue = nullptr;
@@ -76,6 +104,12 @@ struct DevState {
 };
 
 static int S_of(const misob200_params_t &p) { return p.lag > 0 ? (p.n_iters - p.burn_in) / p.lag : 0; }
+// Columns of a gene's sample block: the reference's noSamples = noChains * (noIterations -
+// noBurnIn) / noLag (miso.c:661), which exceeds n_chains * S_of when the lag does not divide
+// the sampling span; the surplus columns stay zero, as in the reference's matrix (miso.c:822).
+static long long cols_of(const misob200_params_t &p) {
+  return p.lag > 0 ? (long long) p.n_chains * (p.n_iters - p.burn_in) / p.lag : 0;
+}
 
 static int check_params(const misob200_params_t &p) {
   if (p.n_iters < 0 || p.burn_in < 0 || p.lag < 1 || p.n_chains < 1 || p.burn_in > p.n_iters) {
@@ -121,7 +155,7 @@ void plan_buckets(const Plan &plan, std::vector<int> (&items)[2 * (kMaxIso + 1)]
 // of samples, then of loglik; entry 2*(kMaxIso+1) is the tail of genes that do not run.
 void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, long long *n_loglik,
                  long long (*range_out)[4]) {
-  const long long S = S_of(p);
+  const long long S = cols_of(p);      // (cache key: columns per gene block)
   long long (*range)[4] = range_out;
   if (plan.lay_chains == p.n_chains && plan.lay_S == S && plan.lay_genes == plan.desc.size()) {
     if (range) std::memcpy(range, plan.lay_range, sizeof(plan.lay_range));
@@ -135,8 +169,8 @@ void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, l
   auto place = [&](int g) {
     plan.desc[g].sample_off = so;
     plan.desc[g].loglik_off = lo;
-    so += (long long) plan.desc[g].K * p.n_chains * S;
-    lo += (long long) p.n_chains * S;
+    so += (long long) plan.desc[g].K * S;
+    lo += S;
   };
   for (int fmt = 0; fmt < 2; fmt++)
     for (int k = kMaxIso; k >= 0; k--) {
@@ -159,7 +193,7 @@ static void free_dev(DevState *st) {
   if (!st) return;
   cudaSetDevice(st->device);
   cudaFree(st->d_tiles); cudaFree(st->d_desc); cudaFree(st->d_ptab); cudaFree(st->d_neglog); cudaFree(st->d_samples);
-  cudaFree(st->d_loglik); cudaFree(st->d_summary); cudaFree(st->d_drawn); cudaFree(st->d_accrej);
+  cudaFree(st->d_loglik); cudaFree(st->d_summary); cudaFree(st->d_compare); cudaFree(st->d_drawn); cudaFree(st->d_accrej);
   cudaFree(st->d_queue); cudaFree(st->d_items); cudaFree(st->d_state); cudaFree(st->d_progress);
   cudaFree(st->d_ring); cudaFree(st->d_ring_tail);
   for (auto &e : st->ev) if (e) cudaEventDestroy(e);
@@ -690,7 +724,7 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
       }
     }
   };
-  unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+  unsigned nt = (unsigned) host_threads();
   if (G < 256) nt = 1;
   if (nt == 1) epilogue(0, G);
   else {
@@ -709,7 +743,7 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
 // numpy's (the module does `from numpy import *`), i.e. half-to-even on the
 // fp64 product; the host computes the two indices with the same expression --
 // plus the per-isoform assigned-read counts of chain 0.
-__global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, int S, int lo, int hi, int n_pad,
+__global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, int n, int lo, int hi, int n_pad,
                                const double *samples, const uint8_t *drawn, const int *accrej,
                                double *summary) {
   extern __shared__ double vals[];
@@ -717,7 +751,7 @@ __global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, 
   if (g >= n_genes) return;
   const GeneDesc &d = desc[g];
   double *out = summary + (size_t) g * MISOB200_SUMMARY_F64;
-  const int n = n_chains * S, K = d.K;
+  const int K = d.K;
   int *iout = reinterpret_cast<int *>(out + 24);
   if (d.status != 0) {
     for (int i = threadIdx.x; i < MISOB200_SUMMARY_F64; i += blockDim.x) out[i] = 0.0;
@@ -787,13 +821,17 @@ __global__ void summary_kernel(const GeneDesc *desc, int n_genes, int n_chains, 
   }
 }
 
-int summarize(Plan &plan, double *summary) {
+// Launches the summary kernel on the plan's stream; the records stay on the device
+// (d_summary, n_genes x 32 f64).  comm.cu all-gathers them from there.
+int summarize_device(Plan &plan, const double **d_summary, cudaStream_t *stream) {
   DevState *st = static_cast<DevState *>(plan.dev);
   if (!st || !st->have_run) { set_error("summarize: nothing has run"); return MISOB200_EINVAL; }
   CK(cudaSetDevice(st->device));
+  if (d_summary) *d_summary = st->d_summary;
+  if (stream) *stream = st->stream;
   const int G = (int) plan.desc.size();
   if (G == 0) return 0;
-  const int S = S_of(st->params), n = st->params.n_chains * S;
+  const int n = (int) cols_of(st->params);      // every column of the block, like the reference's Python (samples_utils.py)
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
   const size_t smem = (size_t) n_pad * sizeof(double);
@@ -801,11 +839,20 @@ int summarize(Plan &plan, double *summary) {
   CK(cudaFuncSetAttribute(summary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   const double alpha = 1 - 0.95;
   const int lo = (int) nearbyint((alpha / 2) * n) - 1, hi = (int) nearbyint((1 - alpha / 2) * n) - 1;
-  summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, S, lo, hi, n_pad, st->d_samples,
+  summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, n, lo, hi, n_pad, st->d_samples,
                                               st->d_drawn, st->d_accrej, st->d_summary);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(summary, st->d_summary, (size_t) G * MISOB200_SUMMARY_F64 * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
-  CK(cudaStreamSynchronize(st->stream));
+  return 0;
+}
+
+int summarize(Plan &plan, double *summary) {
+  const double *d = nullptr;
+  cudaStream_t s = nullptr;
+  if (int rc = summarize_device(plan, &d, &s)) return rc;
+  const size_t G = plan.desc.size();
+  if (G == 0) return 0;
+  CK(cudaMemcpyAsync(summary, d, G * MISOB200_SUMMARY_F64 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return 0;
 }
 
@@ -872,11 +919,13 @@ __global__ void compare_kernel(const GeneDesc *da, const GeneDesc *db, int n_gen
   }
 }
 
-int compare(Plan &pa, Plan &pb, double *out) {
+// Launches compare_kernel on sample A's stream; the records stay on the device in a buffer
+// owned by A's device state (grow-only, no allocation per call).
+int compare_device(Plan &pa, Plan &pb, const double **d_out, cudaStream_t *stream) {
   DevState *a = static_cast<DevState *>(pa.dev), *b = static_cast<DevState *>(pb.dev);
   if (!a || !b || !a->have_run || !b->have_run) { set_error("compare: both plans must have run and stay resident"); return MISOB200_EINVAL; }
   if (a->device != b->device) { set_error("compare: the two samples of an event must live on the same GPU"); return MISOB200_EINVAL; }
-  if (pa.desc.size() != pb.desc.size() || a->params.n_chains != b->params.n_chains || S_of(a->params) != S_of(b->params)) {
+  if (pa.desc.size() != pb.desc.size() || a->params.n_chains != b->params.n_chains || cols_of(a->params) != cols_of(b->params)) {
     set_error("compare: plans differ in events or in the number of recorded samples"); return MISOB200_EINVAL;
   }
   for (size_t g = 0; g < pa.desc.size(); g++)
@@ -886,21 +935,32 @@ int compare(Plan &pa, Plan &pb, double *out) {
     }
   CK(cudaSetDevice(a->device));
   const int G = (int) pa.desc.size();
+  if ((size_t) G > a->compare_cap) {
+    cudaFree(a->d_compare); a->d_compare = nullptr; a->compare_cap = 0;
+    CK(cudaMalloc(&a->d_compare, (size_t) G * MISOB200_COMPARE_F64 * sizeof(double)));
+    a->compare_cap = (size_t) G;
+  }
+  if (d_out) *d_out = a->d_compare;
+  if (stream) *stream = a->stream;
   if (G == 0) return 0;
-  const int n = a->params.n_chains * S_of(a->params);
-  double *d_out = nullptr;
-  CK(cudaMalloc(&d_out, (size_t) G * 32 * sizeof(double)));
-  compare_kernel<<<G, 128, 0, a->stream>>>(a->d_desc, b->d_desc, G, n, a->d_samples, b->d_samples, d_out);
+  const int n = (int) cols_of(a->params);
+  // sample B's kernels ran on B's streams: order after them
+  CK(cudaEventRecord(b->cdone, b->stream));
+  CK(cudaStreamWaitEvent(a->stream, b->cdone, 0));
+  compare_kernel<<<G, 128, 0, a->stream>>>(a->d_desc, b->d_desc, G, n, a->d_samples, b->d_samples, a->d_compare);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(out, d_out, (size_t) G * 32 * sizeof(double), cudaMemcpyDeviceToHost, a->stream));
-  CK(cudaStreamSynchronize(a->stream));
-  cudaFree(d_out);
   return 0;
 }
 
-void *device_summary_ptr(Plan &plan) {
-  DevState *st = static_cast<DevState *>(plan.dev);
-  return st ? st->d_summary : nullptr;
+int compare(Plan &pa, Plan &pb, double *out) {
+  const double *d = nullptr;
+  cudaStream_t s = nullptr;
+  if (int rc = compare_device(pa, pb, &d, &s)) return rc;
+  const size_t G = pa.desc.size();
+  if (G == 0) return 0;
+  CK(cudaMemcpyAsync(out, d, G * MISOB200_COMPARE_F64 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
 }
 
 // per-bucket kernel durations of the last resident run, ms[k] for K = 0..8 (0 when unused)

@@ -68,7 +68,13 @@ def load_gff_genes(path):
             if len(c) < 9:
                 continue
             a = _attrs(c[8])
-            recs.append(GffRecord(c[0], c[1], c[2], int(c[3]), int(c[4]), c[6], a.get("ID"), a.get("Parent")))
+            # multi-valued attributes: the first value counts (gff_utils.py:463-470 get_value);
+            # an exon without ID is named parent@start@end@strand (gff_utils.py:370-376)
+            rid = a["ID"].split(",")[0].rstrip() if "ID" in a else None
+            parent = a["Parent"].split(",")[0].rstrip() if "Parent" in a else None
+            if c[2] == "exon" and rid is None:
+                rid = "%s@%s@%s@%s" % (parent or "", c[3], c[4], c[6])
+            recs.append(GffRecord(c[0], c[1], c[2], int(c[3]), int(c[4]), c[6], rid, parent))
     genes = OrderedDict()
     for r in recs:
         if r.type == "gene":
@@ -278,7 +284,9 @@ def compute_gene_psi(gene_ids, gff_filename, sam_filename, output_dir, read_len,
         gs.append(_batch.Gene(exons, isoforms))
         poss.append([int(p) + 1 for p in reads[0]])                               # miso_sampler.py:284
         cigs.append(list(reads[1]))
-    pe = (float(paired_end[0]), float(paired_end[1]) ** 2, 4.0) if paired_end else (0.0, 0.0, 0.0)
+    # the reference truncates both numbers: mean_frag_len = int(paired_end[0]),
+    # frag_variance = int(paired_end[1]) ** 2 (misopy/run_miso.py:81-83)
+    pe = (float(int(paired_end[0])), float(int(paired_end[1]) ** 2), 4.0) if paired_end else (0.0, 0.0, 0.0)
     rb = _batch.ReadBatch(gs, poss, cigs, int(read_len), int(overhang_len), bool(paired_end), *pe)
     plan = _batch.Plan().append(rb)
     try:

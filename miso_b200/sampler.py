@@ -26,7 +26,9 @@ class GeneModel:
         self.label, self.parts, self.chrom, self.strand = label, list(parts), chrom, strand
         self.isoforms = []
         for desc in isoforms:
-            ps = [p for p in self.parts if p.label in desc]
+            # the first part carrying each label, in the isoform's own order
+            # (misopy/Gene.py:305-321 create_isoforms / get_part_by_label)
+            ps = [next(p for p in self.parts if p.label == lab) for lab in desc]
             self.isoforms.append(Isoform(list(desc), ps, min(p.start for p in ps), max(p.end for p in ps)))
 
 

@@ -28,6 +28,20 @@ def test_every_declared_symbol_is_exported():
     assert set(syms) == set(_lib.EXPORTS)
 
 
+def test_workload_library_exports_its_header():
+    """workloads/libmiso_synth.so (bench / test inputs, outside the product) against include/miso_synth.h."""
+    import workloads
+    src = open(os.path.join(ROOT, "include", "miso_synth.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(misob200_\w+)\s*\(", src)))
+    assert set(syms) == set(workloads.EXPORTS)
+    for s in syms:
+        assert hasattr(workloads.lib, s), s
+    assert C.sizeof(workloads.Reads) == C.sizeof(_lib.Reads)
+    # the product library holds no generator
+    assert not hasattr(_lib.lib, "misob200_workload_create")
+
+
 def test_struct_layouts():
     assert C.sizeof(_lib.Params) == 40
     assert C.sizeof(_lib.Reads) == 4 + 4 + 10 * 8 + 3 * 4 + 4 + 3 * 8

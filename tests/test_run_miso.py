@@ -116,3 +116,50 @@ def test_compute_gene_psi_reproduces_the_golden_posterior(tmp_path):
     assert header["chrom"] == "chr10" and header["strand"] == "+"
     # a second call finds the file and skips the gene (miso_sampler.py:233-238)
     assert rm.compute_gene_psi([EVENT], gff, sam, out_dir, 36, seed=case.seed)[EVENT] == "skipped: output exists"
+
+
+def test_paired_end_insert_model_is_truncated_like_the_reference(monkeypatch):
+    """misopy/run_miso.py:81-83: mean_frag_len = int(mean), frag_variance = int(sd) ** 2 -- miso.py
+    forwards the two numbers as %.1f, so fractional values are normal."""
+    from miso_b200 import run_miso, batch
+    seen = {}
+
+    class Stop(Exception):
+        pass
+
+    def fake_read_batch(gs, poss, cigs, read_len, overhang, paired, mean, var, devs):
+        seen.update(mean=mean, var=var, devs=devs)
+        raise Stop()
+
+    monkeypatch.setattr(batch, "ReadBatch", fake_read_batch)
+    gff = os.path.join(os.path.dirname(__file__), "golden", "_pe_trunc.gff")
+    sam = os.path.join(os.path.dirname(__file__), "golden", "_pe_trunc.sam")
+    try:
+        with open(gff, "w") as f:
+            f.write("chr1\tt\tgene\t1\t1000\t.\t+\t.\tID=g1\n")
+            for t, exons in (("t1", ((1, 100), (301, 400), (601, 700))), ("t2", ((1, 100), (601, 700)))):
+                f.write("chr1\tt\tmRNA\t1\t700\t.\t+\t.\tID=%s;Parent=g1\n" % t)
+                for a, b in exons:
+                    f.write("chr1\tt\texon\t%d\t%d\t.\t+\t.\tParent=%s\n" % (a, b, t))
+        with open(sam, "w") as f:
+            for i in range(30):
+                f.write("r%d\t99\tchr1\t%d\t255\t36M\t=\t%d\t0\t%s\t*\n" % (i, 5 + i, 330 + i, "A" * 36))
+                f.write("r%d\t147\tchr1\t%d\t255\t36M\t=\t%d\t0\t%s\t*\n" % (i, 330 + i, 5 + i, "A" * 36))
+        with pytest.raises(Stop):
+            run_miso.compute_gene_psi(["g1"], gff, sam, os.path.join(os.path.dirname(gff), "_out"), 36,
+                                      paired_end=(251.7, 15.9), settings={"filter_reads": False})
+    finally:
+        for p in (gff, sam):
+            if os.path.exists(p):
+                os.remove(p)
+    assert seen == dict(mean=251.0, var=225.0, devs=4.0)
+
+
+def test_exons_without_id_and_shared_labels():
+    """Exons without an ID attribute are named parent@start@end@strand (gff_utils.py:370-376) and an
+    isoform is the first part carrying each of its labels, in its own order (Gene.py:305-321)."""
+    from miso_b200.sampler import GeneModel, Part
+    parts = [Part("a", 1, 10), Part("b", 20, 30), Part("c", 40, 50), Part("a", 1, 10), Part("c", 40, 50)]
+    g = GeneModel("g", parts, [["a", "b", "c"], ["a", "c"]])
+    assert [len(i.parts) for i in g.isoforms] == [3, 2]
+    assert [p.label for p in g.isoforms[1].parts] == ["a", "c"]

@@ -52,6 +52,29 @@ def test_shard_genes_is_balanced_and_complete():
         assert loads.max() <= loads.mean() * 1.02 + costs.max()
 
 
+def test_bench_deals_one_workload_to_the_ranks():
+    """bench.py --gpus N (strong scaling, BASELINE cfg-4): every event on exactly one rank, every
+    rank the same mix of isoform counts, and a rank's shard regenerates the very genes of the
+    whole workload (a gene is a function of (seed, id))."""
+    import bench
+    from workloads import Workload
+    wl = dict(bench.WORKLOADS["cfg3"], n_genes=3000, reads=20)
+    whole = Workload(wl["kind"], wl["n_genes"], wl["reads"], bench.READ_LEN, *bench.PE, seed=bench.SEED)
+    K = whole.n_iso()
+    for world in (2, 4, 8):
+        parts = [bench.shard_ids(wl, r, world, "strong")[0] for r in range(world)]
+        np.testing.assert_array_equal(np.sort(np.concatenate(parts)), np.arange(3000))
+        cost = np.array([sum(bench.COST_PER_READ[int(k)] for k in K[p]) for p in parts], float)
+        assert cost.max() / cost.mean() < 1.01
+    mine = parts[3]
+    w = Workload(wl["kind"], 0, wl["reads"], bench.READ_LEN, *bench.PE, seed=bench.SEED, gene_ids=mine)
+    for j in (0, len(mine) // 2, len(mine) - 1):
+        a, b = w.gene(j), whole.gene(int(mine[j]))
+        assert a[0] == b[0] and a[1] == b[1] and (a[2] == b[2]).all() and a[3] == b[3]
+    ids, total = bench.shard_ids(wl, 1, 2, "weak")
+    assert total == 6000 and ids[0] == 3000 and len(ids) == 3000
+
+
 def test_gather_with_two_gloo_ranks(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)

@@ -1,4 +1,8 @@
-// miso_b200/csrc/synth.cpp -- synthetic workloads for tests and bench.py.
+// workloads/synth.cpp -- synthetic workloads for tests and bench.py (libmiso_synth.so).
+//
+// Bench / test infrastructure, NOT part of the product library: both arms of bench.py
+// (ours and --impl reference) draw their inputs from here, and the reference arm maps
+// nothing of libmiso_b200.so.
 //
 // Generates the inputs BASELINE.json's configs name:
 //   kind 0  cfg-2: skipped-exon events, K = 2, single-end reads
@@ -20,11 +24,14 @@
 #include <thread>
 #include <vector>
 
-#include "plan.hpp"
+#include "../include/miso_synth.h"
 
 namespace misob200 {
 
 namespace {
+
+thread_local std::string g_synth_error;
+void set_error(const std::string &m) { g_synth_error = m; }
 
 struct Rng {
   uint64_t s;
@@ -84,8 +91,8 @@ struct Workload {
 };
 
 int workload_create(int kind, int n_genes, int reads_per_gene, int read_len, double frag_mean,
-                    double frag_var, double num_devs, uint64_t seed, uint32_t first_gene_id, int n_threads,
-                    Workload **out) {
+                    double frag_var, double num_devs, uint64_t seed, uint32_t first_gene_id,
+                    const uint32_t *gene_ids, uint32_t sample, int n_threads, Workload **out) {
   if (kind != 0 && kind != 1) { set_error("workload kind must be 0 (SE K=2) or 1 (PE mixed K)"); return MISOB200_EINVAL; }
   if (n_genes < 0 || reads_per_gene < 0 || read_len < 4) { set_error("workload: bad sizes"); return MISOB200_EINVAL; }
   Workload *w = new Workload();
@@ -116,7 +123,7 @@ int workload_create(int kind, int n_genes, int reads_per_gene, int read_len, dou
   auto work = [&]() {
     for (int g; (g = next.fetch_add(1)) < n_genes;) {
       GeneBuf &gb = bufs[g];
-      const uint32_t gid = first_gene_id + (uint32_t) g;
+      const uint32_t gid = gene_ids ? gene_ids[g] : first_gene_id + (uint32_t) g;
       Rng rng(seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (gid + 1));
       std::vector<std::vector<int>> iso;    // exon indices per isoform
       std::vector<int> xs, xe;              // exon table
@@ -138,6 +145,8 @@ int workload_create(int kind, int n_genes, int reads_per_gene, int read_len, dou
       }
       const int K = (int) iso.size();
       gb.K = K;
+      // a second sample of the same events (cfg-5): same gene structures, its own psi and reads
+      if (sample) rng = Rng((seed + 0x51ED270B7F4A7C15ull * sample) * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull * (gid + 1));
       // psi ~ Dirichlet(1,...,1)
       gb.psi.resize(K);
       double ps = 0;
@@ -213,7 +222,7 @@ int workload_create(int kind, int n_genes, int reads_per_gene, int read_len, dou
     for (int32_t l : gb.cig_len) w->cigar_off.push_back(w->cigar_off.back() + l);
     w->cigar.insert(w->cigar.end(), gb.cig.begin(), gb.cig.end());
     w->read_off.push_back((int64_t) w->position.size());
-    w->gene_id.push_back(first_gene_id + (uint32_t) g);
+    w->gene_id.push_back(gene_ids ? gene_ids[g] : first_gene_id + (uint32_t) g);
     w->psi.insert(w->psi.end(), gb.psi.begin(), gb.psi.end());
     w->psi_off.push_back((int64_t) w->psi.size());
     std::vector<int32_t>().swap(gb.exon_off);
@@ -231,15 +240,38 @@ struct misob200_workload { Workload *w; };
 
 extern "C" {
 
+const char *misob200_workload_last_error(void) { return misob200::g_synth_error.c_str(); }
+
 int misob200_workload_create(int kind, int32_t n_genes, int32_t reads_per_gene, int32_t read_len,
                              double frag_mean, double frag_var, double num_devs, uint64_t seed,
                              uint32_t first_gene_id, int n_threads, misob200_workload_t **out) {
   if (!out) return MISOB200_EINVAL;
   Workload *w = nullptr;
   int rc = misob200::workload_create(kind, n_genes, reads_per_gene, read_len, frag_mean, frag_var, num_devs,
-                                     seed, first_gene_id, n_threads, &w);
+                                     seed, first_gene_id, nullptr, 0, n_threads, &w);
   if (rc) return rc;
   *out = new misob200_workload{w};
+  return 0;
+}
+
+int misob200_workload_create_ids(int kind, int32_t n_genes, const uint32_t *gene_ids, int32_t reads_per_gene,
+                                 int32_t read_len, double frag_mean, double frag_var, double num_devs,
+                                 uint64_t seed, uint32_t sample, int n_threads, misob200_workload_t **out) {
+  if (!out || (n_genes > 0 && !gene_ids)) return MISOB200_EINVAL;
+  Workload *w = nullptr;
+  int rc = misob200::workload_create(kind, n_genes, reads_per_gene, read_len, frag_mean, frag_var, num_devs,
+                                     seed, 0, gene_ids, sample, n_threads, &w);
+  if (rc) return rc;
+  *out = new misob200_workload{w};
+  return 0;
+}
+
+/* isoform count of every gene of a workload (cheap: no reads are generated when the
+   workload was created with reads_per_gene = 0) */
+int misob200_workload_n_iso(const misob200_workload_t *wl, int32_t *n_iso) {
+  if (!wl || !n_iso) return MISOB200_EINVAL;
+  const Workload &w = *wl->w;
+  for (size_t g = 0; g + 1 < w.iso_off.size(); g++) n_iso[g] = w.iso_off[g + 1] - w.iso_off[g];
   return 0;
 }
 
