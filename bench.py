@@ -314,11 +314,52 @@ def parity_leg(mb, wl, plan, out, ids, per_k=2):
     w.close()
     res = {"genes": len(pick), "oracle": oracle.kind, "counts_bit_exact": exact,
            "max_abs_mean_diff": worst_mean, "max_abs_ci_diff": worst_ci,
-           "what": "per-read assignments and accept/reject counts equal; posterior mean and 95% CI bounds vs the "
+           "what": "per-read assignments and accept/reject counts equal; posterior mean and 95%% CI bounds vs the "
                    "oracle on the same stream, %d genes per isoform count of the timed plan" % per_k}
     if not exact or worst_mean > 1e-3 or worst_ci > 1e-3:
         raise SystemExit("bench.py: PARITY FAILURE on the timed plan: %s" % json.dumps(res))
     return res
+
+
+def writer_leg(mb, plan, out, ids):
+    """Untimed by the step clock, timed by itself: every event of the plan to `<dir>/<chrom>/<event>.miso`
+    through the batched writer (misob200_plan_write_miso; the reference writes file by file from
+    Python, miso_sampler.py:456-465).  Files go to shared memory when the box has it, so the
+    number is the formatter + the file system calls, not a disk."""
+    import shutil
+    import tempfile
+    from miso_b200 import miso_format as mf
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    root = tempfile.mkdtemp(prefix="misob200_bench_", dir=base)
+    try:
+        info = plan.info()
+        G = info.shape[0]
+        chroms = ["chr%d" % (1 + c) for c in range(20)]
+        for c in chroms:
+            os.mkdir(os.path.join(root, c))
+        parts = {}
+        for k in sorted(set(int(x) for x in info[:, 0])):     # the synthetic events of one K share a structure
+            descs = [["E%d" % e for e in range(k + 1) if e != i or i == 0] for i in range(k)]
+            parts[k] = (descs, [("E%d" % e, 200) for e in range(k + 1)], [1] * k, [400 * k + 200] * k)
+        t0 = time.perf_counter()
+        paths, pre, suf = [], [], []
+        for g in range(G):
+            k = int(info[g, 0])
+            c = chroms[g % 20]
+            a, b = mf.header_static_parts(parts[k][0], parts[k][1], c, "+", parts[k][2], parts[k][3])
+            paths.append(os.path.join(root, c, "event%07d.miso" % int(ids[g])))
+            pre.append(a)
+            suf.append(b)
+        t1 = time.perf_counter()
+        nf, nb = plan.write_miso(out, paths, pre, suf)
+        t2 = time.perf_counter()
+        return {"files": int(nf), "bytes": int(nb), "seconds": t2 - t1, "files_per_s": nf / (t2 - t1),
+                "MB_per_s": nb / (t2 - t1) / 1e6, "header_static_parts_s": t1 - t0,
+                "threads": int(mb._lib.lib.misob200_host_threads()), "dir": "shared memory" if base else "tmp dir",
+                "what": "one .miso file per event of rank 0's plan (header + %d posterior samples) from the pinned "
+                        "output buffers" % ((ITERS - BURN) // LAG * CHAINS)}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
 
 
 _JSON_OUT = None
@@ -352,6 +393,7 @@ def main():
     ap.add_argument("--genes", type=int, default=0, help="override the number of events (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-writer", action="store_true")
     ap.add_argument("--cpu-genes-per-core", type=int, default=40)
     ap.add_argument("--ref-genes-per-core-per-step", type=int, default=10)
     ap.add_argument("--match-device", action="store_true", help="plan stage: read<->isoform matching on the GPU")
@@ -528,6 +570,9 @@ def main():
     parity = None
     if rank == 0 and not args.no_parity:
         parity = parity_leg(mb, wl, plans[0], outs[0], ids)
+    writer = None
+    if rank == 0 and not args.no_writer:
+        writer = writer_leg(mb, plans[0], outs[0], ids)
     if world > 1 and wl["samples"] == 1:
         # the gathered table holds every rank's records: all events accounted for
         tab = np.asarray(gathered).reshape(world, n_pad, 32)
@@ -566,6 +611,7 @@ def main():
                          "bucket_ms_per_step": {str(k): bucket[k] / args.steps for k in range(2, 9) if bucket[k] > 0}},
             "cpu_baseline": cpu,
             "parity_checked": parity,
+            "writer": writer,
             "events_per_s_e2e": total_events / (e2e_ms / 1e3),
             "setup_seconds": {"synthetic_generation": t_gen, "host_plan_stage": t_plan},
             "wall_ms_per_resident_step": 1e3 * wall_res / args.steps,

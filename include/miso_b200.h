@@ -110,7 +110,12 @@ typedef struct misob200_params {
  *   assignment: one int32 per read (SE) / pair (PE) in input order, chain 0,
  *               -1 = incompatible (src/miso.c:943-946)
  *   rundata   : 9 int32 per gene, the fields of splicing_miso_rundata_t
- *               (include/splicing.h:143-146) in declaration order
+ *               (include/splicing.h:143-146) in declaration order.  noSamples
+ *               (field 8) = n_chains*S, the columns actually recorded and the
+ *               size of the gene's block; the reference reports
+ *               n_chains*(n_iters-burn_in)/lag (src/miso.c:661), which differs
+ *               when lag does not divide n_iters-burn_in -- its matrix then
+ *               ends in that many all-zero columns, which are not reproduced
  *   status    : 1 int32 per gene, 0 ok, else MISOB200_E*
  */
 
@@ -158,6 +163,9 @@ int misob200_plan_size(const misob200_plan_t *plan, int32_t *n_genes,
 int misob200_plan_gene_info(const misob200_plan_t *plan, int32_t gene,
 			    int32_t *n_iso, int32_t *n_reads, int32_t *n_drawn,
 			    int32_t *n_classes, int32_t *status);
+/* the same for every gene of the plan: info5 = n_genes x {n_iso, n_reads,
+   n_drawn, n_classes, status} */
+int misob200_plan_info_all(const misob200_plan_t *plan, int32_t *info5);
 /* class_templates: n_classes x K doubles, row per class (this is the
    transposed form pysplicing returns, pysplicing.c:120-121); counts likewise.
    SE: exact columns (miso_paired.c:576-619); PE: zero/non-zero patterns
@@ -180,6 +188,10 @@ int misob200_plan_offsets(const misob200_plan_t *plan,
 			  const misob200_params_t *params, int32_t gene,
 			  int64_t *sample_off, int64_t *loglik_off,
 			  int64_t *assign_off);
+int misob200_plan_offsets_all(const misob200_plan_t *plan,
+			      const misob200_params_t *params,
+			      int64_t *sample_off, int64_t *loglik_off,
+			      int64_t *assign_off);
 int misob200_plan_output_sizes(const misob200_plan_t *plan,
 			       const misob200_params_t *params,
 			       int64_t *n_samples_f64, int64_t *n_loglik_f64,
@@ -241,6 +253,40 @@ int misob200_comm_allgather(const double *mine, int64_t n_f64_per_rank,
 			    double *all);
 int misob200_comm_barrier_max(double *value);	/* in: local, out: max */
 int misob200_comm_destroy(void);
+
+/* Batched `.miso` writer (misopy/miso_sampler.py:456-465, one file per event):
+   file i = headers[i] (the "#isoforms=...\n" line, built by the caller) +
+   "sampled_psi\tlog_score\n" + n_rows lines "%.4f,...,%.4f\t%.2f\n" from the
+   event's block of the output buffers of misob200_run (offsets in f64 elements,
+   rows of n_iso[i] psi values).  Formatted and written by n_threads host
+   threads (0: misob200_host_threads()); the directories must exist. */
+int misob200_write_miso_files(int32_t n_files, const char *const *paths,
+			      const char *const *headers,
+			      const double *samples, const int64_t *sample_off,
+			      const double *loglik, const int64_t *loglik_off,
+			      const int32_t *n_iso, int32_t n_rows,
+			      int n_threads, int64_t *bytes_written);
+/* The whole plan at once, headers included: file g = prefix[g] + the
+   run-dependent header fields of misopy/miso_sampler.py:444-454 (iters,
+   burn_in, lag, percent_accept, proposal_type, counts = read classes of the
+   setup stage, assigned_counts = chain 0's assignments per isoform) +
+   suffix[g] + the body as above, from the buffers misob200_run filled.
+   prefix ("#isoforms=[..]\texon_lens=..\t") and suffix ("\tchrom=..\tstrand=..
+   \tmRNA_starts=..\tmRNA_ends=..\n") depend on the annotation only.  Skipped:
+   genes with paths[g] == NULL, status != 0, or no compatible read
+   (miso_sampler.py:352-354). */
+int misob200_plan_write_miso(const misob200_plan_t *plan,
+			     const misob200_params_t *params,
+			     const char *const *paths,
+			     const char *const *prefix,
+			     const char *const *suffix, const double *samples,
+			     const double *loglik, const int32_t *assignment,
+			     const int32_t *rundata, int n_threads,
+			     int64_t *n_written, int64_t *bytes_written);
+/* the writer's number formatting, "%.2f" / "%.4f" (decimals = 2 | 4): exact
+   round-half-even on the binary value, as CPython's "%" operator; returns the
+   length written to out32 (NUL-terminated, at most 31 characters) */
+int misob200_format_fixed(double v, int decimals, char *out32);
 
 /* host worker threads the library uses for the plan stage and the output
    epilogue: MISOB200_HOST_THREADS, else usable cores (affinity, cgroup quota)

@@ -66,6 +66,11 @@ def _load():
     lib.misob200_last_match_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.misob200_plan_size.argtypes = [vp, vp, vp, vp]
     lib.misob200_plan_gene_info.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
+    lib.misob200_plan_info_all.argtypes = [vp, vp]
+    lib.misob200_plan_offsets_all.argtypes = [vp, C.POINTER(Params), vp, vp, vp]
+    lib.misob200_write_miso_files.argtypes = [C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int, vp]
+    lib.misob200_plan_write_miso.argtypes = [vp, C.POINTER(Params), vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp]
+    lib.misob200_format_fixed.argtypes = [C.c_double, C.c_int, vp]
     lib.misob200_plan_gene_classes.argtypes = [vp, C.c_int32, vp, vp]
     lib.misob200_plan_gene_match.argtypes = [vp, C.c_int32, vp, vp]
     lib.misob200_plan_fragment_table.argtypes = [vp, C.c_int32, vp, vp, vp]
@@ -103,7 +108,8 @@ EXPORTS = [
     "misob200_release_device", "misob200_summarize", "misob200_bucket_timing", "misob200_compare",
     "misob200_transfer_bytes", "misob200_comm_unique_id",
     "misob200_comm_init", "misob200_comm_allgather", "misob200_comm_allgather_summaries",
-    "misob200_comm_allgather_compare", "misob200_host_threads", "misob200_comm_barrier_max",
+    "misob200_comm_allgather_compare", "misob200_host_threads",
+    "misob200_plan_info_all", "misob200_plan_offsets_all", "misob200_write_miso_files", "misob200_format_fixed", "misob200_plan_write_miso", "misob200_comm_barrier_max",
     "misob200_comm_destroy", "misob200_host_alloc", "misob200_host_free",
 ]
 

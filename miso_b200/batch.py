@@ -160,13 +160,17 @@ class Plan:
         """int32 array [n_genes, 5]: K, R, R2, n_classes, status."""
         if self._info is None:
             G = self.size()[0]
-            out = np.zeros((G, 5), np.int32)
-            v = [C.c_int32() for _ in range(5)]
-            for g in range(G):
-                check(lib.misob200_plan_gene_info(self.h, g, *[C.addressof(x) for x in v]))
-                out[g] = [x.value for x in v]
-            self._info = out
+            out = np.zeros((max(G, 1), 5), np.int32)
+            check(lib.misob200_plan_info_all(self.h, ptr(out)))
+            self._info = out[:G]
         return self._info
+
+    def offsets(self, params):
+        """int64 arrays (sample_off, loglik_off, assign_off), one entry per gene (elements)."""
+        G = self.size()[0]
+        a, b, c = (np.zeros(max(G, 1), np.int64) for _ in range(3))
+        check(lib.misob200_plan_offsets_all(self.h, C.byref(params), ptr(a), ptr(b), ptr(c)))
+        return a[:G], b[:G], c[:G]
 
     def classes(self, g):
         K, _, _, ncls, _ = self.info()[g]
@@ -249,6 +253,26 @@ class Plan:
         check(lib.misob200_compare(self.h, other.h, ptr(out)))
         return out[:G]
 
+    def write_miso(self, out, paths, prefixes, suffixes, n_threads=0):
+        """Batched ``.miso`` writer (``misob200_plan_write_miso``): one file per gene from the buffers
+        ``run`` filled.  paths[g] None skips a gene; prefixes / suffixes from
+        ``miso_format.header_static_parts``.  Returns (files written, bytes written)."""
+        G = self.size()[0]
+        if not (len(paths) == len(prefixes) == len(suffixes) == G):
+            raise _lib.InternalError("write_miso: one path / prefix / suffix per gene")
+
+        def carr(strs):
+            a = (C.c_char_p * max(G, 1))()
+            for i, t in enumerate(strs):
+                a[i] = None if t is None else (t if isinstance(t, bytes) else str(t).encode())
+            return a
+        pa, pr, su = carr(paths), carr(prefixes), carr(suffixes)
+        nf, nb = C.c_int64(), C.c_int64()
+        check(lib.misob200_plan_write_miso(self.h, C.byref(out["params"]), pa, pr, su, ptr(out["samples"]),
+                                           ptr(out["loglik"]), ptr(out["assignment"]), ptr(out["rundata"]),
+                                           n_threads, C.addressof(nf), C.addressof(nb)))
+        return nf.value, nb.value
+
     def bucket_timing(self):
         ms = np.zeros(9)
         check(lib.misob200_bucket_timing(self.h, ptr(ms)))
@@ -271,7 +295,7 @@ class Plan:
         so, lo, ao = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib.misob200_plan_offsets(self.h, C.byref(p), g, C.addressof(so),
                                         C.addressof(lo), C.addressof(ao)))
-        n = p.n_chains * (p.n_iters - p.burn_in) // p.lag      # the reference's noSamples (miso.c:661)
+        n = p.n_chains * ((p.n_iters - p.burn_in) // p.lag)
         smp = out["samples"][so.value:so.value + K * n].reshape(n, K).T
         return dict(samples=smp, loglik=out["loglik"][lo.value:lo.value + n],
                     assignment=out["assignment"][ao.value:ao.value + R],

@@ -109,6 +109,16 @@ int misob200_plan_gene_info(const misob200_plan_t *plan, int32_t gene, int32_t *
   if (status) *status = h.status;
   return 0;
 }
+/* all genes at once: info5 = n_genes x {K, R, R2, classes, status} */
+int misob200_plan_info_all(const misob200_plan_t *plan, int32_t *info5) {
+  if (!plan || !info5) return MISOB200_EINVAL;
+  const auto &host = plan->p.host;
+  for (size_t g = 0; g < host.size(); g++) {
+    int32_t *o = info5 + 5 * g;
+    o[0] = host[g].K; o[1] = host[g].R; o[2] = host[g].R2; o[3] = host[g].ncls; o[4] = host[g].status;
+  }
+  return 0;
+}
 int misob200_plan_gene_classes(const misob200_plan_t *plan, int32_t gene, double *class_templates,
                                double *class_counts) {
   if (int rc = check_gene(plan, gene)) return rc;
@@ -161,6 +171,19 @@ int misob200_plan_offsets(const misob200_plan_t *plan, const misob200_params_t *
   if (assign_off) *assign_off = p.host[gene].read_base;
   return 0;
 }
+int misob200_plan_offsets_all(const misob200_plan_t *plan, const misob200_params_t *params, int64_t *sample_off,
+                              int64_t *loglik_off, int64_t *assign_off) {
+  if (!plan) return MISOB200_EINVAL;
+  if (plan->p.host.empty()) return 0;
+  if (int rc = misob200_plan_offsets(plan, params, 0, nullptr, nullptr, nullptr)) return rc;     // validates, fills the layout
+  const Plan &p = plan->p;
+  for (size_t g = 0; g < p.desc.size(); g++) {
+    if (sample_off) sample_off[g] = p.desc[g].sample_off;
+    if (loglik_off) loglik_off[g] = p.desc[g].loglik_off;
+    if (assign_off) assign_off[g] = p.host[g].read_base;
+  }
+  return 0;
+}
 int misob200_plan_output_sizes(const misob200_plan_t *plan, const misob200_params_t *params,
                                int64_t *n_samples_f64, int64_t *n_loglik_f64, int64_t *n_assign_i32) {
   if (!plan || !params || params->lag < 1) return MISOB200_EINVAL;
@@ -169,8 +192,7 @@ int misob200_plan_output_sizes(const misob200_plan_t *plan, const misob200_param
     set_error("invalid sampler parameters (iterations/burn-in/lag/chains)");
     return MISOB200_EINVAL;
   }
-  // columns per gene block = the reference's noSamples (miso.c:661)
-  const long long cols = (long long) params->n_chains * (params->n_iters - params->burn_in) / params->lag;
+  const long long cols = (long long) params->n_chains * ((params->n_iters - params->burn_in) / params->lag);
   long long so = 0, lo = 0;
   for (size_t g = 0; g < p.desc.size(); g++) {
     so += (long long) p.desc[g].K * cols;

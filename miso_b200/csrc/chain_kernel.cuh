@@ -113,6 +113,11 @@ struct ChainParams {
   double ptab_min;           // smallest non-zero entry of ptab
   double *samples;
   double *loglik;
+  // optional second destination of every recorded sample: the caller's PINNED host buffers, written
+  // straight over PCIe as the chains produce them (8 K bytes per gene-chain every `lag`
+  // iterations -- ~1.6 GB/s at cfg-3), so a run ends without a device->host copy of the posteriors
+  double *samples_host;
+  double *loglik_host;
   uint8_t *drawn;            // final chain-0 assignment of the reads that draw, draw order
   int *accrej;               // [gene][chain][2]
   unsigned *queue;           // work counter
@@ -454,6 +459,10 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
           const long long col = (long long) n_rec * P.n_chains + chain;
           if (lane < K) P.samples[d.sample_off + col * K + lane] = cur.psi;
           if (lane == 0) P.loglik[d.loglik_off + col] = cJS;
+          if (P.samples_host) {
+            if (lane < K) P.samples_host[d.sample_off + col * K + lane] = cur.psi;
+            if (lane == 0) P.loglik_host[d.loglik_off + col] = cJS;
+          }
         }
         n_rec++;
         lagc = 0;
@@ -487,11 +496,16 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
 // Shared memory: [ptab | per warp {mbarrier (16 B), slot, threshold rows (FMT 1)}].  The slot
 // holds the gene's whole tile (SMEM), or only its class records when the rows are streamed
 // from global/L2 (FMT 1, !SMEM).
-#ifndef MISOB200_MINBLOCKS_CLASS
-#define MISOB200_MINBLOCKS_CLASS 4
-#endif
+// Class-format kernels run as ONE 16-warp CTA per SM (128 registers x 512 threads = the whole
+// register file): an SM then executes a single kernel's code at a time.  The per-iteration
+// instruction footprint of one K is 30-48 KB; with CTAs of several K buckets resident on the same
+// SM the instruction caches thrash and everything runs ~5x slower (profiles/r2_ab1_sched.log),
+// so concurrency between buckets is arranged SM by SM (run.cu, "balanced").  The warps of a CTA
+// stay independent (one __syncthreads at start-up).  Dense-format kernels (rare fallback) keep
+// 4-warp CTAs, 3-4 per SM.
+constexpr int kClassWarps = 16;
 template <int K, int WARPS, bool SMEM, bool WIDE, int FMT>
-__global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? MISOB200_MINBLOCKS_CLASS : (K <= 6 ? 4 : 3))) chain_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? 16 / WARPS : (K <= 6 ? 4 : 3))) chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *s_ptab = reinterpret_cast<double *>(smem);

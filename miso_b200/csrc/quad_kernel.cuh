@@ -311,11 +311,8 @@ __device__ __noinline__ void quad_literal(unsigned gmask, uint32_t rows, const u
 // ---- the kernel ---------------------------------------------------------------------
 // Shared memory per warp: [mbarrier 16 B | 4 x slot (core tile) | 4 x {L_k 32 B, threshold planes}].
 // slot_bytes is 32 mod 128, so the four groups' id words of one step sit in different banks.
-#ifndef MISOB200_MINBLOCKS_QUAD
-#define MISOB200_MINBLOCKS_QUAD 4
-#endif
 template <int K, int WARPS, bool WIDE>
-__global__ void __launch_bounds__(WARPS * 32, MISOB200_MINBLOCKS_QUAD) quad_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) quad_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int len = K - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -493,6 +490,10 @@ __global__ void __launch_bounds__(WARPS * 32, MISOB200_MINBLOCKS_QUAD) quad_kern
             const long long col = (long long) n_rec * P.n_chains + chain;
             if (mi < K) P.samples[d.sample_off + col * K + mi] = cur.psi;
             if (mi == 0) P.loglik[d.loglik_off + col] = cJS;
+            if (P.samples_host) {
+              if (mi < K) P.samples_host[d.sample_off + col * K + mi] = cur.psi;
+              if (mi == 0) P.loglik_host[d.loglik_off + col] = cJS;
+            }
           }
           n_rec++;
           lagc = 0;

@@ -69,13 +69,16 @@ struct DevState {
   // buckets: b = fmt * (kMaxIso + 1) + K, fmt 0 dense tiles, 1 class tiles
   cudaStream_t kstream[kBuckets] = {};      // one per bucket
   cudaEvent_t ev[6] = {};
+  cudaStream_t hstream[kBuckets] = {};      // low priority: a bucket's helper grid (run_resident, "balanced")
   cudaEvent_t kdone[kBuckets] = {};
+  cudaEvent_t kmain[kBuckets] = {};
   cudaEvent_t kbeg[kBuckets] = {}, kend[kBuckets] = {};
   uint8_t *d_tiles = nullptr;
   GeneDesc *d_desc = nullptr;
   double *d_ptab = nullptr, *d_neglog = nullptr;
   int n_neglog = 0;
   double *d_samples = nullptr, *d_loglik = nullptr, *d_summary = nullptr;
+  double *zc_samples = nullptr, *zc_loglik = nullptr;   // device views of the caller's pinned output buffers (this run)
   double *d_compare = nullptr;      // two-sample records (compare_device), grow-only
   size_t compare_cap = 0;           // ... in events
   uint8_t *d_drawn = nullptr;
@@ -85,8 +88,6 @@ struct DevState {
   int *d_progress = nullptr;
   unsigned *d_ring = nullptr, *d_ring_tail = nullptr;
   size_t ring_cap = 0;              // entries
-  int last_n_seg = 1;               // segments of the bucket launched last
-  double last_fill = 0;             // ... and the share of the machine its grid takes
   int *d_items = nullptr;
   std::vector<int> items[kBuckets];
   int item_off[kBuckets + 1] = {};
@@ -104,12 +105,12 @@ struct DevState {
 };
 
 static int S_of(const misob200_params_t &p) { return p.lag > 0 ? (p.n_iters - p.burn_in) / p.lag : 0; }
-// Columns of a gene's sample block: the reference's noSamples = noChains * (noIterations -
-// noBurnIn) / noLag (miso.c:661), which exceeds n_chains * S_of when the lag does not divide
-// the sampling span; the surplus columns stay zero, as in the reference's matrix (miso.c:822).
-static long long cols_of(const misob200_params_t &p) {
-  return p.lag > 0 ? (long long) p.n_chains * (p.n_iters - p.burn_in) / p.lag : 0;
-}
+// Columns of a gene's sample block: n_chains * S.  (The reference sizes its matrix with noSamples =
+// noChains * (noIterations - noBurnIn) / noLag (miso.c:661), which exceeds n_chains * S when the lag does
+// not divide the sampling span and leaves that many all-zero columns behind the recorded ones
+// (miso.c:822); here every column is a recorded sample and rundata.noSamples says n_chains * S --
+// documented deviation, include/miso_b200.h.)
+static long long cols_of(const misob200_params_t &p) { return (long long) p.n_chains * S_of(p); }
 
 static int check_params(const misob200_params_t &p) {
   if (p.n_iters < 0 || p.burn_in < 0 || p.lag < 1 || p.n_chains < 1 || p.burn_in > p.n_iters) {
@@ -198,6 +199,8 @@ static void free_dev(DevState *st) {
   cudaFree(st->d_ring); cudaFree(st->d_ring_tail);
   for (auto &e : st->ev) if (e) cudaEventDestroy(e);
   for (auto &e : st->kdone) if (e) cudaEventDestroy(e);
+  for (auto &e : st->kmain) if (e) cudaEventDestroy(e);
+  for (auto &s : st->hstream) if (s) cudaStreamDestroy(s);
   for (auto &e : st->kbeg) if (e) cudaEventDestroy(e);
   for (auto &e : st->kend) if (e) cudaEventDestroy(e);
   if (!st->h_drawn.empty()) { cudaHostUnregister(st->h_drawn.data()); cudaGetLastError(); }
@@ -298,10 +301,14 @@ int upload(Plan &plan, const misob200_params_t &p) {
   CK(cudaStreamCreateWithFlags(&st->cstream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&st->cdone, cudaEventDisableTiming));
   for (auto &e : st->ev) CK(cudaEventCreate(&e));
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (int b = 0; b < kBuckets; b++) {
     if (b % (kMaxIso + 1) < 2) continue;
-    CK(cudaStreamCreateWithFlags(&st->kstream[b], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&st->kstream[b], cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&st->hstream[b], cudaStreamNonBlocking, prio_lo));
     CK(cudaEventCreateWithFlags(&st->kdone[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&st->kmain[b], cudaEventDisableTiming));
     CK(cudaEventCreate(&st->kbeg[b]));
     CK(cudaEventCreate(&st->kend[b]));
   }
@@ -379,8 +386,6 @@ static void set_segments(ChainParams &P, DevState *st, int b, long long n_units,
   P.seg_len = segment_length(st);
   if (n_units <= n_warps && !std::getenv("MISOB200_SEG_ALWAYS")) P.seg_len = steps;
   P.n_seg = (steps + P.seg_len - 1) / P.seg_len;
-  st->last_n_seg = P.n_seg;
-  st->last_fill = (double) n_warps / (4.0 * 4 * st->sm_count);      // share of the resident warps (4 CTAs x 4 warps per SM)
   P.state = st->d_state;
   P.progress = st->d_progress;
   // bucket b's ring: room for one push per (gene-chain, segment)
@@ -388,15 +393,44 @@ static void set_segments(ChainParams &P, DevState *st, int b, long long n_units,
   P.ring_tail = st->d_ring_tail + b;
 }
 
-#ifndef MISOB200_WARPS
-#define MISOB200_WARPS 4      /* warps per CTA of chain_kernel (A/B builds: 6 with MISOB200_MINBLOCKS_CLASS=3) */
-#endif
+// One bucket, ready to launch: kernel, parameters (all but the segment fields), occupancy.
+struct Launch {
+  const void *kern = nullptr;
+  ChainParams P;
+  size_t smem = 0;
+  int per_sm = 0, warps = 4, b = 0;
+  bool quad = false;
+  long long n_units = 0;       // work units (gene-chains, or groups of four)
+  long long need_blocks = 0;   // CTAs that give every unit a warp
+  double work_ms = 0;          // estimated time on the whole machine (bucket_work_ms)
+  long long blocks = 0;        // CTAs of the main grid
+};
+
+// Estimated whole-machine time of a bucket, ms per 5000 iterations and chain: the measured
+// bucket times of the cfg-3 benchmark (BENCH_r01, ~7.1k genes per isoform count: 24 (four chains
+// per warp) / 71 / 92 / 100 / 118 / 138 / 160 ms) scaled by the drawing reads of each gene
+// -- the scalar part of an iteration costs about as much as the counting pass over 1000 reads
+// (profiles/r1_v8_single_K5_lines.txt).  Only the RATIOS between buckets matter: they set
+// each bucket's share of the SMs; helper grids absorb the error.
+static double bucket_work_ms(const Plan &plan, const std::vector<int> &v, int K, bool quad, bool dense) {
+  static const double ms_per_gene[kMaxIso + 1] = {0, 0, 24.3 / 7012, 70.6 / 7226, 91.7 / 7122, 100.4 / 7083,
+                                                  117.8 / 7168, 137.5 / 7166, 160.3 / 7223};
+  static const double r2_ref[kMaxIso + 1] = {0, 0, 14, 973, 1415, 1557, 1620, 1672, 1708};
+  double c = ms_per_gene[K];
+  if (K == 2 && !quad) c *= 2.4;          // one chain per warp at K = 2: 64 vs 27 ms (r1_ab4)
+  if (K > 2 && quad) c *= 0.9;
+  if (dense) c *= 2.0;
+  double w = 0;
+  for (int g : v) w += c * (1000.0 + plan.desc[g].R2) / (1000.0 + r2_ref[K]);
+  return w;
+}
+
 template <int K, int FMT>
-static int launch_bucket(Plan &plan, DevState *st, int *launches) {
+static int prepare_bucket(Plan &plan, DevState *st, Launch *out) {
   const int b = FMT * (kMaxIso + 1) + K;
   const auto &v = st->items[b];
   if (v.empty()) return 0;
-  constexpr int WARPS = MISOB200_WARPS;
+  constexpr int WARPS = FMT == 1 ? kClassWarps : 4;      // class format: one 16-warp CTA per SM (chain_kernel.cuh)
   // per-warp shared memory: the largest tile of the bucket (+ threshold rows, class format)
   int slot = 0, cls = 0, thr = 0;
   for (int g : v) {
@@ -430,8 +464,6 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
   if (per_sm < 1) { set_error("chain kernel does not fit on an SM"); return MISOB200_ECUDA; }
   const long long n_items = (long long) v.size() * st->params.n_chains;
-  long long blocks = (n_items + WARPS - 1) / WARPS;
-  blocks = std::min<long long>(blocks, (long long) per_sm * st->sm_count);
 
   ChainParams P;
   P.desc = st->d_desc;
@@ -445,6 +477,8 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   for (double v : plan.ptab) if (v > 0 && v < P.ptab_min) P.ptab_min = v;
   P.samples = st->d_samples;
   P.loglik = st->d_loglik;
+  P.samples_host = st->zc_samples;
+  P.loglik_host = st->zc_loglik;
   P.drawn = st->d_drawn;
   P.accrej = st->d_accrej;
   P.queue = st->d_queue + b;
@@ -455,20 +489,22 @@ static int launch_bucket(Plan &plan, DevState *st, int *launches) {
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;
   P.thr_bytes = thr;
-  set_segments(P, st, b, n_items, blocks * WARPS);
-  kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[b]>>>(P);
-  CK(cudaGetLastError());
-  (*launches)++;
+  out->kern = (const void *) kern;
+  out->P = P;
+  out->smem = smem; out->per_sm = per_sm; out->warps = WARPS; out->b = b; out->quad = false;
+  out->n_units = n_items;
+  out->need_blocks = (n_items + WARPS - 1) / WARPS;
+  out->work_ms = bucket_work_ms(plan, v, K, false, FMT == 0) * st->params.n_chains * (st->params.n_iters / 5000.0);
   return 0;
 }
 
 // Four gene-chains per warp (quad_kernel.cuh): class-format buckets whose core tiles fit.
 // Returns 1 when it launched, 0 when the caller should use chain_kernel instead.
 template <int K>
-static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
+static int prepare_quad(Plan &plan, DevState *st, Launch *out, int *rc) {
   const int b = (kMaxIso + 1) + K;
   const auto &v = st->items[b];
-  constexpr int WARPS = 4;
+  constexpr int WARPS = kClassWarps;
   int core = 0, thr = 0;
   for (int g : v) {
     const GeneDesc &d = plan.desc[g];
@@ -502,8 +538,6 @@ static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem);
   if (per_sm < 1) { cudaGetLastError(); *rc = 0; return 0; }
   const long long n_items = (long long) v.size() * st->params.n_chains;
-  long long blocks = (n_items + WARPS * kQuad - 1) / (WARPS * kQuad);
-  blocks = std::min<long long>(blocks, (long long) per_sm * st->sm_count);
 
   ChainParams P;
   P.desc = st->d_desc;
@@ -517,6 +551,8 @@ static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
   for (double v : plan.ptab) if (v > 0 && v < P.ptab_min) P.ptab_min = v;
   P.samples = st->d_samples;
   P.loglik = st->d_loglik;
+  P.samples_host = st->zc_samples;
+  P.loglik_host = st->zc_loglik;
   P.drawn = st->d_drawn;
   P.accrej = st->d_accrej;
   P.queue = st->d_queue + b;
@@ -527,38 +563,46 @@ static int launch_quad(Plan &plan, DevState *st, int *launches, int *rc) {
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;
   P.thr_bytes = thr;
-  set_segments(P, st, b, (n_items + kQuad - 1) / kQuad, blocks * WARPS);
-  kern<<<(unsigned) blocks, WARPS * 32, smem, st->kstream[b]>>>(P);
-  if (cudaGetLastError() != cudaSuccess) { set_error("quad kernel launch failed"); return 1; }
-  (*launches)++;
+  out->kern = (const void *) kern;
+  out->P = P;
+  out->smem = smem; out->per_sm = per_sm; out->warps = WARPS; out->b = b; out->quad = true;
+  out->n_units = (n_items + kQuad - 1) / kQuad;
+  out->need_blocks = (out->n_units + WARPS - 1) / WARPS;
+  out->work_ms = bucket_work_ms(plan, v, K, true, false) * st->params.n_chains * (st->params.n_iters / 5000.0);
   *rc = 0;
   return 1;
 }
 
-static int launch_quad_k(Plan &plan, DevState *st, int k, int *nl, int *rc) {
+static int prepare_quad_k(Plan &plan, DevState *st, int k, Launch *nl, int *rc) {
   switch (k) {
-    case 2: return launch_quad<2>(plan, st, nl, rc);
-    case 3: return launch_quad<3>(plan, st, nl, rc);
-    case 4: return launch_quad<4>(plan, st, nl, rc);
-    case 5: return launch_quad<5>(plan, st, nl, rc);
-    case 6: return launch_quad<6>(plan, st, nl, rc);
-    case 7: return launch_quad<7>(plan, st, nl, rc);
-    case 8: return launch_quad<8>(plan, st, nl, rc);
+    case 2: return prepare_quad<2>(plan, st, nl, rc);
+    case 3: return prepare_quad<3>(plan, st, nl, rc);
+    case 4: return prepare_quad<4>(plan, st, nl, rc);
+    case 5: return prepare_quad<5>(plan, st, nl, rc);
+    case 6: return prepare_quad<6>(plan, st, nl, rc);
+    case 7: return prepare_quad<7>(plan, st, nl, rc);
+    case 8: return prepare_quad<8>(plan, st, nl, rc);
   }
   return 0;
 }
 
 template <int FMT>
-static int launch_k(Plan &plan, DevState *st, int k, int *nl) {
+static int prepare_k(Plan &plan, DevState *st, int k, Launch *nl) {
   switch (k) {
-    case 2: return launch_bucket<2, FMT>(plan, st, nl);
-    case 3: return launch_bucket<3, FMT>(plan, st, nl);
-    case 4: return launch_bucket<4, FMT>(plan, st, nl);
-    case 5: return launch_bucket<5, FMT>(plan, st, nl);
-    case 6: return launch_bucket<6, FMT>(plan, st, nl);
-    case 7: return launch_bucket<7, FMT>(plan, st, nl);
-    case 8: return launch_bucket<8, FMT>(plan, st, nl);
+    case 2: return prepare_bucket<2, FMT>(plan, st, nl);
+    case 3: return prepare_bucket<3, FMT>(plan, st, nl);
+    case 4: return prepare_bucket<4, FMT>(plan, st, nl);
+    case 5: return prepare_bucket<5, FMT>(plan, st, nl);
+    case 6: return prepare_bucket<6, FMT>(plan, st, nl);
+    case 7: return prepare_bucket<7, FMT>(plan, st, nl);
+    case 8: return prepare_bucket<8, FMT>(plan, st, nl);
   }
+  return 0;
+}
+
+static int fire(Launch &L, long long blocks, cudaStream_t stream) {
+  void *args[] = {&L.P};
+  CK(cudaLaunchKernel(L.kern, dim3((unsigned) blocks), dim3(L.warps * 32), args, L.smem, stream));
   return 0;
 }
 
@@ -589,6 +633,21 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
   CK(cudaMemsetAsync(st->d_samples, 0, std::max<long long>(st->n_samples, 1) * sizeof(double), st->stream));
   CK(cudaMemsetAsync(st->d_loglik, 0, std::max<long long>(st->n_loglik, 1) * sizeof(double), st->stream));
   CK(cudaEventRecord(st->ev[2], st->stream));
+  // Pinned output buffers are written by the kernels themselves (ChainParams.samples_host):
+  // nothing is left to copy when the chains end.  Pageable buffers get the device->host copies.
+  st->zc_samples = st->zc_loglik = nullptr;
+  bool zc = false;
+  if (h_samples && h_loglik && !std::getenv("MISOB200_NO_ZEROCOPY")) {
+    cudaPointerAttributes pa, pl;
+    if (cudaPointerGetAttributes(&pa, h_samples) == cudaSuccess && cudaPointerGetAttributes(&pl, h_loglik) == cudaSuccess &&
+        pa.type == cudaMemoryTypeHost && pl.type == cudaMemoryTypeHost && pa.devicePointer && pl.devicePointer) {
+      zc = true;
+      st->zc_samples = static_cast<double *>(pa.devicePointer);
+      st->zc_loglik = static_cast<double *>(pl.devicePointer);
+    } else {
+      cudaGetLastError();
+    }
+  }
   int rc = 0;
   // development only (tools/ab_bench.py): time one isoform-count bucket by itself; the
   // other genes' outputs are then left unset
@@ -607,40 +666,122 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
     const char *cpw = std::getenv("MISOB200_CHAINS_PER_WARP");
     if (cpw) quad = std::atoi(cpw) == 4;
   }
-  int prev = -1;
   // dense buckets first (slowest per read), big K before small K (longest chains)
-  const bool small_first = std::getenv("MISOB200_SMALL_K_FIRST") != nullptr;
+  std::vector<Launch> Ls;
   for (int fmt = 0; fmt < 2 && !rc; fmt++)
-    for (int kk = kMaxIso; kk >= 2 && !rc; kk--) {
-      const int k = small_first ? kMaxIso + 2 - kk : kk;
+    for (int k = kMaxIso; k >= 2 && !rc; k--) {
       const int b = fmt * (kMaxIso + 1) + k;
       if (st->items[b].empty()) continue;
       if (only_k && k != only_k) continue;
-      CK(cudaStreamWaitEvent(st->kstream[b], st->ev[2], 0));
-      // A bucket that fills most of the machine runs alone and the next one starts after it: two
-      // different kernels sharing the SMs cost more than the idle share and the tail -- short,
-      // when the bucket is cut into segments (measured, profiles/r1_ab10/ab11).  Small buckets
-      // overlap with each other.
-      if (prev >= 0 && !concurrent_all) CK(cudaStreamWaitEvent(st->kstream[b], st->kdone[prev], 0));
-      CK(cudaEventRecord(st->kbeg[b], st->kstream[b]));
-      if (!(fmt && quad && launch_quad_k(plan, st, k, &nl, &rc)))
-        rc = fmt ? launch_k<1>(plan, st, k, &nl) : launch_k<0>(plan, st, k, &nl);
+      Launch L;
+      if (!(fmt && quad && prepare_quad_k(plan, st, k, &L, &rc))) rc = fmt ? prepare_k<1>(plan, st, k, &L) : prepare_k<0>(plan, st, k, &L);
       if (rc) return rc;
+      Ls.push_back(L);
+    }
+  // Launch policy for the class-format buckets.  "balanced" (default): every bucket gets a share of
+  // the SMs in proportion to its estimated work and all buckets run side by side from start to
+  // end, each on its own SMs (one 16-warp CTA per SM, chain_kernel.cuh) and cut into segments
+  // where it has more units than warps -- no bucket waits for another, one tail per step instead
+  // of one per bucket, and a small batch (a rank's shard of a workload dealt to several GPUs)
+  // still fills the machine.  Behind the main grids every bucket gets a low-priority HELPER grid
+  // on the same work queue: the block scheduler places its CTAs on the SMs that fall free when
+  // some bucket ends before the others (the estimate is only that), and they exit at once
+  // when their bucket has nothing left.
+  // "serial" (MISOB200_SCHED=serial, round 1): buckets that fill the machine one after the other.
+  // Dense-format buckets (rare fallback, 4-warp CTAs) always run first, one after the other.
+  const char *sched = std::getenv("MISOB200_SCHED");
+  std::vector<Launch *> cls;
+  for (auto &L : Ls) if (L.b > kMaxIso) cls.push_back(&L);
+  const bool balanced = !(sched && std::strcmp(sched, "serial") == 0) && !serial && !concurrent_all && cls.size() > 1;
+  if (balanced) {
+    const long long slots = st->sm_count;
+    double total = 0;
+    for (auto *L : cls) total += L->work_ms;
+    // water-filling: a bucket never gets more CTAs than it has units for; what it leaves goes to the rest
+    std::vector<char> capped(cls.size(), 0);
+    long long free_slots = slots;
+    double open = total;
+    for (bool again = true; again;) {
+      again = false;
+      for (size_t i = 0; i < cls.size(); i++) {
+        if (capped[i]) continue;
+        const double want = open > 0 ? cls[i]->work_ms / open * free_slots : 0;
+        if ((double) cls[i]->need_blocks <= want) {
+          cls[i]->blocks = cls[i]->need_blocks; capped[i] = 1;
+          free_slots -= cls[i]->blocks; open -= cls[i]->work_ms; again = true;
+        }
+      }
+    }
+    // largest-remainder rounding of the open buckets' shares, at least one SM each
+    long long given = 0;
+    std::vector<std::pair<double, size_t>> rem;
+    for (size_t i = 0; i < cls.size(); i++)
+      if (!capped[i]) {
+        const double want = cls[i]->work_ms / open * free_slots;
+        cls[i]->blocks = std::max<long long>(1, (long long) want);
+        given += cls[i]->blocks;
+        rem.push_back({want - (double) (long long) want, i});
+      }
+    std::sort(rem.begin(), rem.end(), [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &c) { return a.first > c.first; });
+    for (size_t r = 0; r < rem.size() && given < free_slots; r++, given++) cls[rem[r].second]->blocks++;
+  }
+  int prev = -1;
+  for (auto &L : Ls) {
+    const int b = L.b;
+    const bool bal = balanced && b > kMaxIso;
+    CK(cudaStreamWaitEvent(st->kstream[b], st->ev[2], 0));
+    if (!bal) {
+      L.blocks = std::min<long long>(L.need_blocks, (long long) L.per_sm * st->sm_count);
+      // A bucket that fills most of the machine runs alone and the next one starts after it
+      // (measured, profiles/r1_ab10/ab11).  Small buckets overlap with each other.
+      if (prev >= 0 && !concurrent_all) CK(cudaStreamWaitEvent(st->kstream[b], st->kdone[prev], 0));
+    } else if (prev >= 0) {
+      CK(cudaStreamWaitEvent(st->kstream[b], st->kdone[prev], 0));      // after the dense buckets
+    }
+    set_segments(L.P, st, b, L.n_units, L.blocks * L.warps);
+    CK(cudaEventRecord(st->kbeg[b], st->kstream[b]));
+    if (int r = fire(L, L.blocks, st->kstream[b])) return r;
+    nl++;
+    CK(cudaEventRecord(st->kmain[b], st->kstream[b]));
+    if (!bal) {
       CK(cudaEventRecord(st->kend[b], st->kstream[b]));
       CK(cudaEventRecord(st->kdone[b], st->kstream[b]));
-      // a finished bucket's posteriors are one contiguous range (plan_layout): copy them out
-      // while the later buckets run
-      if (h_samples || h_loglik) {
-        CK(cudaStreamWaitEvent(st->cstream, st->kdone[b], 0));
-        const long long *r = st->range[b];
-        if (h_samples && r[1] > r[0])
-          CK(cudaMemcpyAsync(h_samples + r[0], st->d_samples + r[0], (r[1] - r[0]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
-        if (h_loglik && r[3] > r[2])
-          CK(cudaMemcpyAsync(h_loglik + r[2], st->d_loglik + r[2], (r[3] - r[2]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
-      }
-      if (serial || st->last_n_seg > 1 || st->last_fill >= 0.6) prev = b;
-      CK(cudaStreamWaitEvent(st->stream, st->kdone[b], 0));
+      const double fill = (double) (L.blocks * L.warps) / ((double) L.per_sm * L.warps * st->sm_count);
+      if (serial || b <= kMaxIso || L.P.n_seg > 1 || fill >= 0.6) prev = b;
     }
+  }
+  if (balanced) {
+    // helper grids, biggest bucket first (largest absolute error of the estimate)
+    std::vector<Launch *> order(cls);
+    std::stable_sort(order.begin(), order.end(), [](const Launch *a, const Launch *c) { return a->work_ms > c->work_ms; });
+    for (Launch *L : order) {
+      const int b = L->b;
+      CK(cudaStreamWaitEvent(st->hstream[b], st->ev[2], 0));
+      if (prev >= 0) CK(cudaStreamWaitEvent(st->hstream[b], st->kdone[prev], 0));
+      if (L->n_units > L->blocks * L->warps) {      // (a bucket with a warp per unit has nothing to hand out)
+        const long long hb = std::min<long long>(L->need_blocks - L->blocks, (long long) L->per_sm * st->sm_count);
+        if (int r = fire(*L, hb, st->hstream[b])) return r;
+        nl++;
+      }
+      CK(cudaStreamWaitEvent(st->hstream[b], st->kmain[b], 0));
+      CK(cudaEventRecord(st->kend[b], st->hstream[b]));
+      CK(cudaEventRecord(st->kdone[b], st->hstream[b]));
+    }
+  }
+  for (auto &L : Ls) {
+    const int b = L.b;
+    // a finished bucket's posteriors are one contiguous range (plan_layout): copy them out
+    // while the other buckets run
+    if ((h_samples || h_loglik) && !zc) {
+      CK(cudaStreamWaitEvent(st->cstream, st->kdone[b], 0));
+      const long long *r = st->range[b];
+      if (h_samples && r[1] > r[0])
+        CK(cudaMemcpyAsync(h_samples + r[0], st->d_samples + r[0], (r[1] - r[0]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
+      if (h_loglik && r[3] > r[2])
+        CK(cudaMemcpyAsync(h_loglik + r[2], st->d_loglik + r[2], (r[3] - r[2]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
+    }
+    CK(cudaStreamWaitEvent(st->stream, st->kdone[b], 0));
+  }
   CK(cudaEventRecord(st->ev[3], st->stream));
   if (h_samples || h_loglik) {
     // genes that did not run (status != 0): their zeroed blocks, the tail of the layout; and
@@ -649,6 +790,11 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
       const bool ran = b < kBuckets && !st->items[b].empty() && !(only_k && b % (kMaxIso + 1) != only_k);
       if (ran) continue;
       const long long *r = st->range[b];
+      if (zc) {
+        if (r[1] > r[0]) std::memset(h_samples + r[0], 0, (r[1] - r[0]) * sizeof(double));
+        if (r[3] > r[2]) std::memset(h_loglik + r[2], 0, (r[3] - r[2]) * sizeof(double));
+        continue;
+      }
       CK(cudaStreamWaitEvent(st->cstream, st->ev[2], 0));
       if (h_samples && r[1] > r[0])
         CK(cudaMemcpyAsync(h_samples + r[0], st->d_samples + r[0], (r[1] - r[0]) * sizeof(double), cudaMemcpyDeviceToHost, st->cstream));
@@ -712,7 +858,7 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
         int32_t *rd = rundata + g * 9;
         rd[0] = h.K; rd[1] = p.n_iters; rd[2] = 0; rd[3] = p.burn_in; rd[4] = p.lag;
         rd[5] = acc; rd[6] = rej; rd[7] = p.n_chains;
-        rd[8] = (int) ((long long) p.n_chains * (p.n_iters - p.burn_in) / p.lag);
+        rd[8] = (int) cols_of(p);
       }
       if (assignment) {
         int32_t *a = assignment + h.read_base;

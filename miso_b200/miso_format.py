@@ -20,26 +20,34 @@ def count_isoform_assignments(assignments):
     return [(k, int((a == k).sum())) for k in range(n + 1)]
 
 
-def format_header(isoform_descs, exon_lens, iters, burn_in, lag, percent_accept, proposal_type,
-                  read_classes, read_class_counts, assignments, chrom=None, strand=None,
-                  mRNA_starts=(), mRNA_ends=()):
-    """Header line of a .miso file (``miso_sampler.py:385-454``)."""
+def header_static_parts(isoform_descs, exon_lens, chrom=None, strand=None, mRNA_starts=(), mRNA_ends=()):
+    """The two pieces of a .miso header line that depend on the annotation only
+    (``miso_sampler.py:385-403,430-454``): ("#isoforms=..\texon_lens=..\t", "\tchrom=..\n").  The
+    batched writer (``misob200_plan_write_miso``) fills in the run-dependent fields between them."""
     if len(isoform_descs) and isinstance(isoform_descs[0], (list, tuple)):
         str_isoforms = "[" + ",".join("'" + "_".join(d) + "'" for d in isoform_descs) + "]"
     else:
         str_isoforms = "[" + ",".join("'" + d + "'" for d in isoform_descs) + "]"
     exon_lens_s = ",".join("('%s',%d)" % (label, length) for label, length in exon_lens)
+    prefix = "#isoforms=%s\texon_lens=%s\t" % (str_isoforms, exon_lens_s)
+    suffix = "\tchrom=%s\tstrand=%s\tmRNA_starts=%s\tmRNA_ends=%s\n" % (
+        "NA" if chrom is None else chrom, "NA" if strand is None else strand,
+        ",".join(str(s) for s in mRNA_starts), ",".join(str(e) for e in mRNA_ends))
+    return prefix, suffix
+
+
+def format_header(isoform_descs, exon_lens, iters, burn_in, lag, percent_accept, proposal_type,
+                  read_classes, read_class_counts, assignments, chrom=None, strand=None,
+                  mRNA_starts=(), mRNA_ends=()):
+    """Header line of a .miso file (``miso_sampler.py:385-454``)."""
+    prefix, suffix = header_static_parts(isoform_descs, exon_lens, chrom, strand, mRNA_starts, mRNA_ends)
     counts = []
     for cls, cnt in zip(read_classes, read_class_counts):
         counts.append("%s:%s" % (str(tuple(int(c) for c in cls)).replace(" ", ""), int(cnt)))
     assigned = ",".join("%d:%d" % c for c in count_isoform_assignments(assignments))
-    return ("#isoforms=%s\texon_lens=%s\titers=%d\tburn_in=%d\tlag=%d\t"
-            "percent_accept=%.2f\tproposal_type=%s\t"
-            "counts=%s\tassigned_counts=%s\tchrom=%s\tstrand=%s\tmRNA_starts=%s\tmRNA_ends=%s\n"
-            % (str_isoforms, exon_lens_s, iters, burn_in, lag, percent_accept, proposal_type,
-               ",".join(counts), assigned, "NA" if chrom is None else chrom,
-               "NA" if strand is None else strand,
-               ",".join(str(s) for s in mRNA_starts), ",".join(str(e) for e in mRNA_ends)))
+    return (prefix + "iters=%d\tburn_in=%d\tlag=%d\tpercent_accept=%.2f\tproposal_type=%s\t"
+            "counts=%s\tassigned_counts=%s" % (iters, burn_in, lag, percent_accept, proposal_type,
+                                              ",".join(counts), assigned) + suffix)
 
 
 def write_miso(path, header, psi_vectors, log_scores):

@@ -4,6 +4,7 @@ misopy/credible_intervals.py:4-55."""
 import os
 
 import numpy as np
+import pytest
 
 from miso_b200 import miso_format as mf
 
@@ -132,3 +133,126 @@ def test_cli_summarize_and_compare(tmp_path, capsys):
     run_miso.main(["--compare-samples", str(tmp_path / "s1"), str(tmp_path / "s2"), str(tmp_path / "out")])
     assert (tmp_path / "out" / "s1_vs_s2" / "bayes-factors" / "s1_vs_s2.miso_bf").is_file()
     assert "1 events" in capsys.readouterr().out
+
+
+# ---- batched writer (miso_b200/csrc/writer.cpp) -------------------------------------------------
+
+def test_fixed_point_formatting_equals_python_percent_operator():
+    """The writer's "%.4f" / "%.2f": round-half-even on the exact binary value, as CPython's "%"
+    (miso_sampler.py:461-463), incl. exact ties (multiples of 1/32, x.125), signs, non-finite."""
+    import ctypes as C
+    from miso_b200._lib import lib
+    buf = C.create_string_buffer(64)
+    rng = np.random.default_rng(3)
+    vals = list(rng.random(20000)) + list(-rng.random(5000) * 1e5) + [k / 32 for k in range(-64, 64)]
+    vals += [(2 * m + 1) * 625 / 20000.0 for m in range(500)] + [(2 * m + 1) / 8.0 for m in range(200)]
+    vals += [0.0, -0.0, 1.0, 0.99995, 0.00005, 1e-300, -1e-9, 123456.785, float("inf"), float("-inf"), float("nan"), 1e15]
+    for v in vals:
+        for d, fmt in ((2, "%.2f"), (4, "%.4f")):
+            n = lib.misob200_format_fixed(float(v), d, buf)
+            assert buf.value.decode() == fmt % v and n == len(fmt % v), (v, d)
+
+
+def test_batched_writer_equals_the_python_writer(tmp_path):
+    """misob200_plan_write_miso on a whole plan = format_header + write_miso gene by gene, byte for byte
+    (plan and layout are host-side; the output buffers are filled with random posteriors here)."""
+    import miso_b200 as mb
+    w = mb.Workload(1, 40, 120, 36, 250.0, 900.0, 4.0, seed=4)
+    plan = mb.Plan().append(w)
+    params = mb.make_params(300, 60, 7, 2, seed=1)
+    G = plan.size()[0]
+    info = plan.info()
+    ns, nl, na = plan.output_sizes(params)
+    rng = np.random.default_rng(9)
+    out = dict(samples=rng.random(ns), loglik=-rng.random(nl) * 5000, params=params,
+               assignment=np.zeros(na, np.int32), rundata=np.zeros((G, 9), np.int32), status=np.zeros(G, np.int32))
+    so, lo, ao = plan.offsets(params)
+    for g in range(G):
+        K, R = int(info[g, 0]), int(info[g, 1])
+        out["assignment"][ao[g]:ao[g] + R] = rng.integers(-1, K, size=R)
+        out["rundata"][g, 5:7] = (rng.integers(1, 300), rng.integers(0, 300))
+    out["assignment"][ao[3]:ao[3] + int(info[3, 1])] = -1           # no compatible read: no file (miso_sampler.py:352-354)
+    metas, paths, pre, suf = [], [], [], []
+    for g in range(G):
+        K = int(info[g, 0])
+        descs = [["e%d" % e for e in range(K + 1) if e != k or k == 0] for k in range(K)]
+        meta = dict(isoform_descs=descs, exon_lens=[("e%d" % e, 200) for e in range(K + 1)], chrom="chr%d" % (g % 3),
+                    strand="+-"[g % 2], mRNA_starts=[1] * K, mRNA_ends=[400 * K + 200] * K)
+        metas.append(meta)
+        a, b = mf.header_static_parts(**meta)
+        pre.append(a)
+        suf.append(b)
+        paths.append(None if g == 5 else str(tmp_path / ("g%d.miso" % g)))
+    nf, nb = plan.write_miso(out, paths, pre, suf, n_threads=3)
+    assert nf == G - 2 and not os.path.exists(str(tmp_path / "g3.miso")) and not os.path.exists(str(tmp_path / "g5.miso"))
+    total = 0
+    for g in range(G):
+        if g in (3, 5):
+            continue
+        r = plan.gene_result(out, g)
+        templ, counts = plan.classes(g)
+        acc, rej = int(r["rundata"][5]), int(r["rundata"][6])
+        m = metas[g]
+        header = mf.format_header(m["isoform_descs"], m["exon_lens"], 300, 60, 7, float(acc) / (acc + rej) * 100, "drift",
+                                  templ, counts, r["assignment"], m["chrom"], m["strand"], m["mRNA_starts"], m["mRNA_ends"])
+        ref = str(tmp_path / "ref.miso")
+        mf.write_miso(ref, header, r["samples"].T, r["loglik"])
+        want = open(ref, "rb").read()
+        got = open(paths[g], "rb").read()
+        assert got == want, "gene %d" % g
+        total += len(got)
+    assert nb == total
+
+
+REF_MISO = "/root/reference/misopy/sashimi_plot/test-data/miso-data"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MISO), reason="the reference tree is not mounted on this box")
+def test_reference_held_miso_files_round_trip(tmp_path):
+    """SURVEY.md section 8c fixture 4: the four .miso files the reference ships.  The parser reads them, the
+    summary numbers equal an independent numpy computation on the raw text, and both writers re-emit
+    header and psi column byte for byte (the reference wrote them with the same format strings)."""
+    import glob
+    import ctypes as C
+    from miso_b200._lib import lib, ptr
+    files = sorted(glob.glob(os.path.join(REF_MISO, "*", "chr17", "*.miso")))
+    assert len(files) == 4
+    for path in files:
+        raw = open(path).read()
+        lines = raw.splitlines()
+        samples, header, scores, smap, smap_score, counts = mf.load_samples(path)
+        body = [ln.split("\t") for ln in lines[2:]]
+        psi = np.array([[float(v) for v in b[0].split(",")] for b in body])
+        np.testing.assert_array_equal(samples, psi)
+        np.testing.assert_array_equal(scores, np.array([float(b[1]) for b in body]))
+        assert set(header) >= {"isoforms", "exon_lens", "iters", "burn_in", "lag", "percent_accept", "proposal_type",
+                               "counts", "assigned_counts"}
+        assert counts == header["counts"] and samples.shape[1] == 2
+        # summary fields (credible_intervals.py:4-28): mean and order statistics
+        n = len(psi)
+        srt = np.sort(psi[:, 0])
+        lo, hi = int(np.round(0.025 * n)) - 1, int(np.round(0.975 * n)) - 1
+        assert mf.format_credible_intervals("ev", samples) == ["ev", "%.2f" % psi[:, 0].mean(), "%.2f" % srt[lo], "%.2f" % srt[hi]]
+        # python writer: header, column line and the psi column byte for byte; these legacy files carry
+        # the log score with four decimals, the current writer (miso_sampler.py:461-463) prints two
+        def same_but_score_decimals(text):
+            got = text.splitlines()
+            assert got[:2] == lines[:2] and len(got) == len(lines)
+            for a, b in zip(got[2:], lines[2:]):
+                (pa, sa), (pb, sb) = a.split("\t"), b.split("\t")
+                assert pa == pb and sa == "%.2f" % float(sb)
+        out = str(tmp_path / "py.miso")
+        mf.write_miso(out, lines[0] + "\n", samples, scores)
+        same_but_score_decimals(open(out).read())
+        # batched C++ writer, same bytes
+        out2 = str(tmp_path / "cc.miso")
+        s = np.ascontiguousarray(samples, np.float64)
+        sc = np.ascontiguousarray(scores, np.float64)
+        off = np.zeros(1, np.int64)
+        k = np.array([2], np.int32)
+        pa = (C.c_char_p * 1)(out2.encode())
+        hd = (C.c_char_p * 1)((lines[0] + "\n").encode())
+        nb = C.c_int64()
+        assert lib.misob200_write_miso_files(1, pa, hd, ptr(s), ptr(off), ptr(sc), ptr(off), ptr(k), n, 1, C.addressof(nb)) == 0
+        same_but_score_decimals(open(out2).read())
+        assert open(out2).read() == open(out).read() and nb.value == os.path.getsize(out)

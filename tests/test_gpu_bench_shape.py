@@ -35,7 +35,8 @@ def test_benchmark_workload_matches_oracle(mb, ref_or_port, monkeypatch, name, p
     ids = np.arange(wl["n_genes"], dtype=np.uint32)
     plan, _, _ = bench.build_plan(mb, wl, ids)
     params = mb.make_params(bench.ITERS, bench.BURN, bench.LAG, bench.CHAINS, seed=bench.SEED)
-    out = plan.run(params)
+    out = plan.alloc_outputs(params, pinned=True)      # as bench.py: the kernels write the posteriors to host memory themselves
+    plan.run(params, out)
     assert (out["status"] == 0).all()
     assert (out["rundata"][:, 5] + out["rundata"][:, 6] == bench.ITERS).all()
     info = plan.info()
@@ -54,12 +55,3 @@ def test_benchmark_workload_matches_oracle(mb, ref_or_port, monkeypatch, name, p
     # the bench's own parity leg agrees (what BENCH's parity_checked field reports)
     res = bench.parity_leg(mb, wl, plan, out, ids, per_k=1)
     assert res["counts_bit_exact"] and res["max_abs_mean_diff"] <= 1e-3 and res["max_abs_ci_diff"] <= 1e-3
-
-
-def test_strong_scaling_shards_cover_the_workload(mb):
-    """bench.py --gpus N deals ONE workload: every event on exactly one rank, costs level."""
-    wl = dict(bench.WORKLOADS["cfg3"], n_genes=4000)
-    for world in (2, 8):
-        parts = [bench.shard_ids(wl, r, world, "strong")[0] for r in range(world)]
-        np.testing.assert_array_equal(np.sort(np.concatenate(parts)), np.arange(4000))
-        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 0.05 * 4000 / world
