@@ -15,6 +15,7 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
 int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, int32_t *rundata,
              int32_t *status);
 int release_device(Plan &plan);
+int release_pool();
 int summarize(Plan &plan, double *summary);
 int run_timing(Plan &plan, double *timing_ms);
 int device_count(int *n);
@@ -33,7 +34,7 @@ int misob200_version(void) { return 100; }
 const char *misob200_last_error(void) { return last_error(); }
 
 int misob200_init(int device) { return device_init(device); }
-int misob200_shutdown(void) { return 0; }
+int misob200_shutdown(void) { return release_pool(); }
 int misob200_device_count(int *count) { return device_count(count); }
 
 int misob200_plan_create(misob200_plan_t **plan) {

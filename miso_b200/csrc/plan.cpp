@@ -19,6 +19,8 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -104,6 +106,25 @@ struct ColCmp {           // include/matrix.pmt:546-561 on ptab[code]
   }
 };
 
+static std::atomic<long long> g_prof[8];
+struct ProfT {
+  int slot; std::chrono::steady_clock::time_point t0;
+  explicit ProfT(int s) : slot(s), t0(std::chrono::steady_clock::now()) {}
+  void next(int s) { auto t = std::chrono::steady_clock::now(); g_prof[slot] += std::chrono::duration_cast<std::chrono::nanoseconds>(t - t0).count(); slot = s; t0 = t; }
+  ~ProfT() { next(slot); }
+};
+// The same order from one integer comparison: every code is replaced by the dense rank of its
+// probability (equal probabilities -- the two tails of a symmetric insert model -- share a rank),
+// 16 bits per isoform, isoform 0 most significant.  BMSort sees exactly the comparison results
+// ColCmp would give, so the (unstable) tie order is unchanged.
+struct KeyCmp {
+  const unsigned __int128 *key;
+  int operator()(int32_t a, int32_t b) const {
+    const unsigned __int128 x = key[a], y = key[b];
+    return x < y ? -1 : (x > y ? 1 : 0);
+  }
+};
+
 struct GeneOut {
   GeneHost h;
   GeneDesc d;
@@ -140,6 +161,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
       isolen[k] += gv.ex_end[e] - gv.ex_start[e] + 1;
   }
 
+  ProfT prof(0);
   // ---- compatibility codes, K x R column-major --------------------------
   // match_core.hpp; either computed here, or taken from the device kernel (match.cu), which
   // compiles the same functions
@@ -158,12 +180,25 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   }
   // odd trailing mate of a paired batch is ignored, as noreads/2 does (solve.c:187)
 
+  prof.next(1);
   // ---- draw order ---------------------------------------------------------
   std::vector<int32_t> order(R);
   for (int r = 0; r < R; r++) order[r] = r;
-  BMSort<ColCmp> sorter{ColCmp{codes.data(), plan.ptab.data(), K}};
-  sorter.sort(order.data(), R);
+  if ((int) plan.code_rank.size() == n_codes && !std::getenv("MISOB200_SORT_DOUBLES")) {
+    std::vector<unsigned __int128> key(R > 0 ? R : 1);
+    for (int r = 0; r < R; r++) {
+      unsigned __int128 v = 0;
+      for (int k = 0; k < K; k++) v = (v << 16) | plan.code_rank[codes[(size_t) r * K + k]];
+      key[r] = v;
+    }
+    BMSort<KeyCmp> sorter{KeyCmp{key.data()}};
+    sorter.sort(order.data(), R);
+  } else {
+    BMSort<ColCmp> sorter{ColCmp{codes.data(), plan.ptab.data(), K}};
+    sorter.sort(order.data(), R);
+  }
 
+  prof.next(2);
   // ---- read classes: histogram over zero/non-zero patterns ---------------
   // Both reference tabulations list distinct patterns in ascending
   // lexicographic order with isoform 0 most significant
@@ -228,6 +263,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
     return -std::log(lp) + plan.ptab[code];                  // miso_paired.c:411
   };
 
+  prof.next(3);
   // ---- split reads into fixed and drawn; pack the tile ------------------------
   h.fixed_ass.assign(R, -1);
   h.rank_read.clear();
@@ -249,8 +285,10 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
     }
     h.fixed_ass[r] = -2;
     drawn.push_back(r);
+    // a score is finite unless its length term is log of a non-positive number
+    // (ptab entries are finite): no need to evaluate the logarithm to know
     for (int k = 0; k < K; k++)
-      if (col[k] && !std::isfinite(read_score(k, col[k]))) d.rp_always = 1;
+      if (col[k] && (paired ? d.L[k] - (col[k] - 1) <= 0 : d.L[k] <= 0)) d.rp_always = 1;
   }
   const int R2 = (int) drawn.size();
   h.R2 = R2; d.R2 = R2;
@@ -263,6 +301,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   // (n_codes, appended on upload) in place of the code.  Other reads key on their
   // full code vector.  class_kernel.cuh turns each class into K-1 integer thresholds
   // on the raw Philox word once per iteration.
+  prof.next(4);
   const int one_idx = n_codes;
   std::vector<uint8_t> cls_id(R2);
   std::vector<uint16_t> ucode(R2, 0);
@@ -272,6 +311,8 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   if (class_ok) {
     std::unordered_map<std::string, int> seen;
     std::string key(2 * kMaxIso, '\0');
+    std::array<uint16_t, kMaxIso> prev{};
+    int prev_id = -1;
     for (int i = 0; i < R2 && class_ok; i++) {
       const int32_t *col = codes.data() + (size_t) drawn[i] * K;
       int32_t common = 0;
@@ -284,17 +325,22 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
       std::array<uint16_t, kMaxIso> v{};
       for (int k = 0; k < K; k++) v[k] = (uint16_t) (col[k] ? (uniform ? one_idx : col[k]) : 0);
       ucode[i] = uniform ? (uint16_t) common : 0;
-      std::memcpy(&key[0], v.data(), 2 * kMaxIso);
-      auto it = seen.find(key);
       int id;
-      if (it == seen.end()) {
-        id = (int) cls_keys.size();
-        if (id >= kMaxClasses) { class_ok = false; break; }
-        seen.emplace(key, id);
-        cls_keys.push_back(v);
-        cls_size.push_back(0);
+      if (prev_id >= 0 && v == prev) {      // the draw order is sorted by column: runs of one class
+        id = prev_id;
       } else {
-        id = it->second;
+        std::memcpy(&key[0], v.data(), 2 * kMaxIso);
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+          id = (int) cls_keys.size();
+          if (id >= kMaxClasses) { class_ok = false; break; }
+          seen.emplace(key, id);
+          cls_keys.push_back(v);
+          cls_size.push_back(0);
+        } else {
+          id = it->second;
+        }
+        prev = v; prev_id = id;
       }
       cls_id[i] = (uint8_t) id;
       cls_size[id]++;
@@ -317,6 +363,7 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
     for (int i = 0; i < R2; i++) cls_id[i] = (uint8_t) to[cls_id[i]];
   }
 
+  prof.next(5);
   const int cb = plan.wide ? 2 : 1;
   const int padded = round_up(R2 + kTilePadFront, 128);
   if (class_ok) {
@@ -441,6 +488,21 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
     return MISOB200_EINVAL;
   }
 
+  if (plan.code_rank.size() != plan.ptab.size()) {
+    // dense rank of every code's probability (KeyCmp)
+    const int n = (int) plan.ptab.size();
+    std::vector<int> by(n);
+    for (int i = 0; i < n; i++) by[i] = i;
+    std::stable_sort(by.begin(), by.end(), [&](int a, int b) { return plan.ptab[a] < plan.ptab[b]; });
+    plan.code_rank.assign(n, 0);
+    int rank = 0;
+    for (int i = 0; i < n; i++) {
+      if (i && plan.ptab[by[i]] != plan.ptab[by[i - 1]]) rank++;
+      plan.code_rank[by[i]] = (uint16_t) rank;
+    }
+    if (n > 65535) plan.code_rank.clear();      // (never: kMaxCodes)
+  }
+
   const int G = in.n_genes;
   // optional: read <-> isoform compatibility on the GPU
   DeviceCodes dev_codes;
@@ -465,6 +527,7 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
     for (int t = 0; t < nt; t++) pool.emplace_back(work);
     for (auto &t : pool) t.join();
   }
+  auto t_merge = std::chrono::steady_clock::now();
   for (int g = 0; g < G; g++) {
     GeneOut &o = outs[g];
     o.h.read_base = plan.n_reads;
@@ -477,6 +540,12 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
     plan.desc.push_back(o.d);
     plan.host.push_back(std::move(o.h));
     std::vector<uint8_t>().swap(o.tile);
+  }
+  if (std::getenv("MISOB200_PLAN_PROFILE")) {
+    const double merge = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_merge).count();
+    fprintf(stderr, "[plan profile] thread-seconds: match %.3f sort %.3f classes %.3f consts+split %.3f weight classes %.3f tile %.3f; merge (serial) %.3f s\n",
+            g_prof[0] / 1e9, g_prof[1] / 1e9, g_prof[2] / 1e9, g_prof[3] / 1e9, g_prof[4] / 1e9, g_prof[5] / 1e9, merge);
+    for (auto &x : g_prof) x = 0;
   }
   return 0;
 }

@@ -72,6 +72,7 @@ struct Plan {
   double frag_mean = 0, frag_var = 0, num_devs = 0;
   int frag_start = 0, frag_len_n = 0;
   std::vector<double> ptab;              // ptab[0] = 0, ptab[j+1] = fragment prob j (SE: {0,1})
+  std::vector<uint16_t> code_rank;       // dense rank of ptab[code] (plan.cpp KeyCmp: the draw-order sort key)
   bool wide = false;                     // more than 255 fragment lengths: 16-bit codes
   int force_format = -1;                 // tests: 0 = dense tiles only, 1 = class tiles whenever possible (default)
   std::vector<GeneDesc> desc;

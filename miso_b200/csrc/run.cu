@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -99,10 +100,46 @@ struct DevState {
   bool pinned_tiles = false, pinned_desc = false;
   std::vector<double> h_ptab;       // plan.ptab + the 1.0 of the uniform-code classes
   std::vector<double> h_neglog;     // -log(n), read scores of the class format
-  std::vector<uint8_t> h_drawn;
-  std::vector<int> h_accrej;
+  uint8_t *h_drawn = nullptr;       // pinned staging of the drawn assignments / accept counters (grow-only)
+  int *h_accrej = nullptr;
+  size_t cap_h_drawn = 0, cap_h_accrej = 0;
+  // capacities (bytes) of the grow-only device buffers: a released state goes back to a small pool
+  // and serves the next plan without a cudaMalloc (drop-in calls run one gene per plan)
+  size_t cap_tiles = 0, cap_desc = 0, cap_ptab = 0, cap_neglog = 0, cap_samples = 0, cap_loglik = 0, cap_summary = 0,
+         cap_drawn = 0, cap_accrej = 0, cap_state = 0, cap_progress = 0, cap_items = 0;
   int sm_count = 0;
+  size_t device_bytes() const {
+    return cap_tiles + cap_desc + cap_ptab + cap_neglog + cap_samples + cap_loglik + cap_summary + cap_drawn +
+           cap_accrej + cap_state + cap_progress + cap_items + ring_cap * sizeof(unsigned) + compare_cap * 256;
+  }
 };
+
+// Released device states of small plans, kept for the next plan on the same GPU: streams, events,
+// device buffers and pinned staging survive, so back-to-back pysplicing.MISO calls (one gene per
+// plan, the way misopy/run_miso.py drives the sampler) pay no allocation after the first.
+static std::mutex g_pool_mu;
+static std::vector<DevState *> g_pool;
+constexpr size_t kPoolMaxStates = 4, kPoolMaxBytes = 64u << 20;
+
+template <class T>
+static int ensure_dev(T *&p, size_t &cap, size_t need_bytes) {
+  need_bytes = std::max<size_t>(need_bytes, 16);
+  if (need_bytes <= cap) return 0;
+  cudaFree(p); p = nullptr; cap = 0;
+  CK(cudaMalloc(&p, need_bytes));
+  cap = need_bytes;
+  return 0;
+}
+template <class T>
+static int ensure_pinned(T *&p, size_t &cap, size_t need_bytes) {
+  need_bytes = std::max<size_t>(need_bytes, 16);
+  if (need_bytes <= cap) return 0;
+  if (p) cudaFreeHost(p);
+  p = nullptr; cap = 0;
+  CK(cudaHostAlloc(&p, need_bytes, cudaHostAllocDefault));
+  cap = need_bytes;
+  return 0;
+}
 
 static int S_of(const misob200_params_t &p) { return p.lag > 0 ? (p.n_iters - p.burn_in) / p.lag : 0; }
 // Columns of a gene's sample block: n_chains * S.  (The reference sizes its matrix with noSamples =
@@ -203,7 +240,8 @@ static void free_dev(DevState *st) {
   for (auto &s : st->hstream) if (s) cudaStreamDestroy(s);
   for (auto &e : st->kbeg) if (e) cudaEventDestroy(e);
   for (auto &e : st->kend) if (e) cudaEventDestroy(e);
-  if (!st->h_drawn.empty()) { cudaHostUnregister(st->h_drawn.data()); cudaGetLastError(); }
+  if (st->h_drawn) cudaFreeHost(st->h_drawn);
+  if (st->h_accrej) cudaFreeHost(st->h_accrej);
   for (auto &s : st->kstream) if (s) cudaStreamDestroy(s);
   if (st->stream) cudaStreamDestroy(st->stream);
   if (st->cstream) cudaStreamDestroy(st->cstream);
@@ -216,9 +254,26 @@ int release_device(Plan &plan) {
   if (st) {
     if (st->pinned_tiles) cudaHostUnregister(plan.tiles.data());
     if (st->pinned_desc) cudaHostUnregister(plan.desc.data());
-    free_dev(st);
+    st->pinned_tiles = st->pinned_desc = false;
+    st->uploaded = st->have_run = false;
+    bool pooled = false;
+    if (st->device_bytes() <= kPoolMaxBytes) {
+      std::lock_guard<std::mutex> lock(g_pool_mu);
+      if (g_pool.size() < kPoolMaxStates) { g_pool.push_back(st); pooled = true; }
+    }
+    if (!pooled) free_dev(st);
   }
   plan.dev = nullptr;
+  return 0;
+}
+
+int release_pool() {
+  std::vector<DevState *> all;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    all.swap(g_pool);
+  }
+  for (DevState *st : all) free_dev(st);
   return 0;
 }
 
@@ -290,28 +345,37 @@ int upload(Plan &plan, const misob200_params_t &p) {
   rc = device_init(p.device);
   if (rc) return rc;
   release_device(plan);
-  DevState *st = new DevState();
-  plan.dev = st;
-  st->device = p.device;
-  st->params = p;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, p.device));
-  st->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&st->cstream, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&st->cdone, cudaEventDisableTiming));
-  for (auto &e : st->ev) CK(cudaEventCreate(&e));
-  int prio_lo = 0, prio_hi = 0;
-  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-  for (int b = 0; b < kBuckets; b++) {
-    if (b % (kMaxIso + 1) < 2) continue;
-    CK(cudaStreamCreateWithPriority(&st->kstream[b], cudaStreamNonBlocking, prio_hi));
-    CK(cudaStreamCreateWithPriority(&st->hstream[b], cudaStreamNonBlocking, prio_lo));
-    CK(cudaEventCreateWithFlags(&st->kdone[b], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&st->kmain[b], cudaEventDisableTiming));
-    CK(cudaEventCreate(&st->kbeg[b]));
-    CK(cudaEventCreate(&st->kend[b]));
+  DevState *st = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (size_t i = 0; i < g_pool.size(); i++)
+      if (g_pool[i]->device == p.device) { st = g_pool[i]; g_pool.erase(g_pool.begin() + i); break; }
   }
+  CK(cudaSetDevice(p.device));
+  if (!st) {
+    st = new DevState();
+    st->device = p.device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, p.device));
+    st->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&st->cstream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&st->cdone, cudaEventDisableTiming));
+    for (auto &e : st->ev) CK(cudaEventCreate(&e));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    for (int b = 0; b < kBuckets; b++) {
+      if (b % (kMaxIso + 1) < 2) continue;
+      CK(cudaStreamCreateWithPriority(&st->kstream[b], cudaStreamNonBlocking, prio_hi));
+      CK(cudaStreamCreateWithPriority(&st->hstream[b], cudaStreamNonBlocking, prio_lo));
+      CK(cudaEventCreateWithFlags(&st->kdone[b], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&st->kmain[b], cudaEventDisableTiming));
+      CK(cudaEventCreate(&st->kbeg[b]));
+      CK(cudaEventCreate(&st->kend[b]));
+    }
+  }
+  plan.dev = st;
+  st->params = p;
 
   plan_layout(plan, p, &st->n_samples, &st->n_loglik, st->range);
   const size_t G = plan.desc.size();
@@ -340,30 +404,30 @@ int upload(Plan &plan, const misob200_params_t &p) {
   }
 
   const size_t tile_bytes = plan.tiles.size();
-  CK(cudaMalloc(&st->d_tiles, std::max<size_t>(tile_bytes, 16)));
-  CK(cudaMalloc(&st->d_desc, std::max<size_t>(G, 1) * sizeof(GeneDesc)));
-  CK(cudaMalloc(&st->d_ptab, st->h_ptab.size() * sizeof(double)));
-  CK(cudaMalloc(&st->d_neglog, st->h_neglog.size() * sizeof(double)));
-  CK(cudaMalloc(&st->d_samples, std::max<long long>(st->n_samples, 1) * sizeof(double)));
-  CK(cudaMalloc(&st->d_loglik, std::max<long long>(st->n_loglik, 1) * sizeof(double)));
-  CK(cudaMalloc(&st->d_summary, std::max<size_t>(G, 1) * MISOB200_SUMMARY_F64 * sizeof(double)));
-  CK(cudaMalloc(&st->d_drawn, std::max<long long>(plan.n_drawn, 16)));
-  CK(cudaMalloc(&st->d_accrej, std::max<size_t>(G, 1) * p.n_chains * 2 * sizeof(int)));
-  CK(cudaMalloc(&st->d_queue, kBuckets * sizeof(unsigned)));
-  CK(cudaMalloc(&st->d_state, std::max<size_t>(G, 1) * p.n_chains * sizeof(ChainState)));
-  CK(cudaMalloc(&st->d_progress, std::max<size_t>(G, 1) * p.n_chains * sizeof(int)));
-  CK(cudaMalloc(&st->d_ring_tail, kBuckets * sizeof(unsigned)));
-  CK(cudaMalloc(&st->d_items, std::max(total, 1) * sizeof(int)));
+  const size_t GC = std::max<size_t>(G, 1) * p.n_chains;
+  if (int r = ensure_dev(st->d_tiles, st->cap_tiles, tile_bytes)) return r;
+  if (int r = ensure_dev(st->d_desc, st->cap_desc, G * sizeof(GeneDesc))) return r;
+  if (int r = ensure_dev(st->d_ptab, st->cap_ptab, st->h_ptab.size() * sizeof(double))) return r;
+  if (int r = ensure_dev(st->d_neglog, st->cap_neglog, st->h_neglog.size() * sizeof(double))) return r;
+  if (int r = ensure_dev(st->d_samples, st->cap_samples, (size_t) st->n_samples * sizeof(double))) return r;
+  if (int r = ensure_dev(st->d_loglik, st->cap_loglik, (size_t) st->n_loglik * sizeof(double))) return r;
+  if (int r = ensure_dev(st->d_summary, st->cap_summary, std::max<size_t>(G, 1) * MISOB200_SUMMARY_F64 * sizeof(double))) return r;
+  if (int r = ensure_dev(st->d_drawn, st->cap_drawn, (size_t) plan.n_drawn)) return r;
+  if (int r = ensure_dev(st->d_accrej, st->cap_accrej, GC * 2 * sizeof(int))) return r;
+  if (int r = ensure_dev(st->d_state, st->cap_state, GC * sizeof(ChainState))) return r;
+  if (int r = ensure_dev(st->d_progress, st->cap_progress, GC * sizeof(int))) return r;
+  if (int r = ensure_dev(st->d_items, st->cap_items, (size_t) std::max(total, 1) * sizeof(int))) return r;
+  if (!st->d_queue) CK(cudaMalloc(&st->d_queue, kBuckets * sizeof(unsigned)));
+  if (!st->d_ring_tail) CK(cudaMalloc(&st->d_ring_tail, kBuckets * sizeof(unsigned)));
 
-  // pin the plan's arenas once so the per-run H2D runs at link speed
-  if (tile_bytes && cudaHostRegister(plan.tiles.data(), tile_bytes, cudaHostRegisterDefault) == cudaSuccess)
+  // pin the plan's arenas once so the per-run H2D runs at link speed (small plans: not worth the call)
+  if (tile_bytes >= (1u << 20) && cudaHostRegister(plan.tiles.data(), tile_bytes, cudaHostRegisterDefault) == cudaSuccess)
     st->pinned_tiles = true;
-  if (G && cudaHostRegister(plan.desc.data(), G * sizeof(GeneDesc), cudaHostRegisterDefault) == cudaSuccess)
+  if (tile_bytes >= (1u << 20) && G && cudaHostRegister(plan.desc.data(), G * sizeof(GeneDesc), cudaHostRegisterDefault) == cudaSuccess)
     st->pinned_desc = true;
   cudaGetLastError();
-  st->h_drawn.resize(std::max<long long>(plan.n_drawn, 1));
-  st->h_accrej.resize(std::max<size_t>(G, 1) * p.n_chains * 2);
-  if (cudaHostRegister(st->h_drawn.data(), st->h_drawn.size(), cudaHostRegisterDefault) != cudaSuccess) cudaGetLastError();
+  if (int r = ensure_pinned(st->h_drawn, st->cap_h_drawn, (size_t) plan.n_drawn)) return r;
+  if (int r = ensure_pinned(st->h_accrej, st->cap_h_accrej, GC * 2 * sizeof(int))) return r;
   return copy_inputs(plan, st);
 }
 
@@ -600,8 +664,22 @@ static int prepare_k(Plan &plan, DevState *st, int k, Launch *nl) {
   return 0;
 }
 
-static int fire(Launch &L, long long blocks, cudaStream_t stream) {
+// cluster > 1: the grid is launched as thread-block clusters of that many CTAs, which the hardware
+// places on neighbouring SMs (a pair shares a TPC) -- the kernels do not use the cluster, it only
+// keeps the SMs of one bucket together (run_resident, "balanced").
+static int fire(Launch &L, long long blocks, cudaStream_t stream, int cluster = 1) {
   void *args[] = {&L.P};
+  if (cluster > 1 && blocks % cluster == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) blocks); cfg.blockDim = dim3(L.warps * 32);
+    cfg.dynamicSmemBytes = L.smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned) cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelExC(&cfg, L.kern, args));
+    return 0;
+  }
   CK(cudaLaunchKernel(L.kern, dim3((unsigned) blocks), dim3(L.warps * 32), args, L.smem, stream));
   return 0;
 }
@@ -693,6 +771,11 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
   std::vector<Launch *> cls;
   for (auto &L : Ls) if (L.b > kMaxIso) cls.push_back(&L);
   const bool balanced = !(sched && std::strcmp(sched, "serial") == 0) && !serial && !concurrent_all && cls.size() > 1;
+  // main grids go out as clusters of two CTAs = whole TPCs: the two SMs of a TPC share an
+  // instruction cache level, and pairs running different buckets cost ~3 % of the step
+  // (profiles/r2_ab3_sched_cluster.log: 770 -> 748 ms; clusters of four were slower)
+  const char *cl_env = std::getenv("MISOB200_CLUSTER");
+  const int cluster = cl_env ? std::max(1, std::atoi(cl_env)) : 2;
   if (balanced) {
     const long long slots = st->sm_count;
     double total = 0;
@@ -724,6 +807,17 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
       }
     std::sort(rem.begin(), rem.end(), [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &c) { return a.first > c.first; });
     for (size_t r = 0; r < rem.size() && given < free_slots; r++, given++) cls[rem[r].second]->blocks++;
+    if (cluster > 1) {      // whole clusters: round every share to a multiple, the largest bucket takes the difference
+      long long sum = 0;
+      Launch *big = cls[0];
+      for (auto *L : cls) {
+        L->blocks = std::max<long long>(cluster, (L->blocks + cluster / 2) / cluster * cluster);
+        sum += L->blocks;
+        if (L->work_ms > big->work_ms) big = L;
+      }
+      const long long usable = slots / cluster * cluster;
+      if (sum != usable && big->blocks + (usable - sum) >= cluster) big->blocks += usable - sum;
+    }
   }
   int prev = -1;
   for (auto &L : Ls) {
@@ -740,7 +834,7 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
     }
     set_segments(L.P, st, b, L.n_units, L.blocks * L.warps);
     CK(cudaEventRecord(st->kbeg[b], st->kstream[b]));
-    if (int r = fire(L, L.blocks, st->kstream[b])) return r;
+    if (int r = fire(L, L.blocks, st->kstream[b], bal ? cluster : 1)) return r;
     nl++;
     CK(cudaEventRecord(st->kmain[b], st->kstream[b]));
     if (!bal) {
@@ -835,9 +929,9 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
   if (loglik && st->n_loglik)
     CK(cudaMemcpyAsync(loglik, st->d_loglik, st->n_loglik * sizeof(double), cudaMemcpyDeviceToHost, st->stream));
   if (assignment && plan.n_drawn)
-    CK(cudaMemcpyAsync(st->h_drawn.data(), st->d_drawn, plan.n_drawn, cudaMemcpyDeviceToHost, st->stream));
+    CK(cudaMemcpyAsync(st->h_drawn, st->d_drawn, plan.n_drawn, cudaMemcpyDeviceToHost, st->stream));
   if (G)
-    CK(cudaMemcpyAsync(st->h_accrej.data(), st->d_accrej, G * p.n_chains * 2 * sizeof(int), cudaMemcpyDeviceToHost, st->stream));
+    CK(cudaMemcpyAsync(st->h_accrej, st->d_accrej, G * p.n_chains * 2 * sizeof(int), cudaMemcpyDeviceToHost, st->stream));
   CK(cudaEventRecord(st->ev[5], st->stream));
   CK(cudaStreamSynchronize(st->stream));
 
@@ -864,7 +958,7 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
         int32_t *a = assignment + h.read_base;
         for (int r = 0; r < h.R; r++) a[r] = h.status == 0 ? h.fixed_ass[r] : -1;
         if (h.status == 0) {
-          const uint8_t *dr = st->h_drawn.data() + d.drawn_off;
+          const uint8_t *dr = st->h_drawn + d.drawn_off;
           for (int i = 0; i < h.R2; i++) a[h.rank_read[i]] = dr[i];
         }
       }

@@ -1,0 +1,22 @@
+"""Drop-in call latency: 100 consecutive single-gene pysplicing.MISOPaired calls at the reference's
+default run parameters.  Device state (streams, events, buffers, pinned staging) is pooled across
+plans (run.cu), so only the first call pays for it."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+
+def test_hundred_consecutive_single_gene_calls():
+    import miso_b200
+    if miso_b200.device_count() < 1:
+        pytest.fail("no CUDA device visible: the gpu tests must run on a B200")
+    import dropin_latency
+    r = dropin_latency.measure(100, reads=2000, kind=1)
+    print("drop-in latency:", r)
+    # one chain is 5000 dependent iterations (tens of ms on a warp); the reference needs ~2 s per call
+    assert r["mean_ms_after_first"] < 400, r
+    assert r["max_ms_after_first"] < 3 * r["median_ms"] + 50, r
