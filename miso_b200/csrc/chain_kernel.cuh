@@ -503,9 +503,12 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
 // so concurrency between buckets is arranged SM by SM (run.cu, "balanced").  The warps of a CTA
 // stay independent (one __syncthreads at start-up).  Dense-format kernels (rare fallback) keep
 // 4-warp CTAs, 3-4 per SM.
-constexpr int kClassWarps = 16;
+#ifndef MISOB200_CLASS_WARPS
+#define MISOB200_CLASS_WARPS 16      /* A/B builds: 20 (96 registers) with MISOB200_PASS_NOINLINE */
+#endif
+constexpr int kClassWarps = MISOB200_CLASS_WARPS;
 template <int K, int WARPS, bool SMEM, bool WIDE, int FMT>
-__global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? 16 / WARPS : (K <= 6 ? 4 : 3))) chain_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? 1 : (K <= 6 ? 4 : 3))) chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *s_ptab = reinterpret_cast<double *>(smem);

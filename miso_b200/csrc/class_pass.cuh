@@ -258,8 +258,13 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
   }
 }
 
+#ifdef MISOB200_PASS_NOINLINE
+#define MISOB200_PASS_INLINE __noinline__
+#else
+#define MISOB200_PASS_INLINE __forceinline__
+#endif
 template <int K, bool SMEM>
-__device__ __forceinline__ void class_pass(typename TileMem<SMEM>::addr_t rows, const ClassRef &cr,
+__device__ MISOB200_PASS_INLINE void class_pass(typename TileMem<SMEM>::addr_t rows, const ClassRef &cr,
                                            unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
                                            const PhiloxKey &key, const int *__restrict__ g_always, int (&cnt)[K]) {
   double unused;

@@ -312,7 +312,7 @@ __device__ __noinline__ void quad_literal(unsigned gmask, uint32_t rows, const u
 // Shared memory per warp: [mbarrier 16 B | 4 x slot (core tile) | 4 x {L_k 32 B, threshold planes}].
 // slot_bytes is 32 mod 128, so the four groups' id words of one step sit in different banks.
 template <int K, int WARPS, bool WIDE>
-__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) quad_kernel(const __grid_constant__ ChainParams P) {
+__global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int len = K - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
