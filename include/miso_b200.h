@@ -97,7 +97,7 @@ typedef struct misob200_params {
   int32_t stop;			/* MISOB200_STOP_FIXEDNO only */
   int32_t algo;			/* MISOB200_ALGO_REASSIGN only */
   int32_t device;		/* CUDA ordinal               */
-  uint64_t seed;		/* stream = Philox4x32-10 keyed (seed; gene_id, chain) */
+  uint64_t seed;		/* stream = Philox4x32 keyed (seed; gene_id, chain) */
 } misob200_params_t;
 
 /* per-gene layout of the outputs of misob200_run (all caller-owned):
@@ -287,6 +287,15 @@ int misob200_plan_write_miso(const misob200_plan_t *plan,
    round-half-even on the binary value, as CPython's "%" operator; returns the
    length written to out32 (NUL-terminated, at most 31 characters) */
 int misob200_format_fixed(double v, int decimals, char *out32);
+
+/* The random stream ("same seed" is defined by this framework, the reference
+   never seeds): Philox4x32 keyed (seed; gene_id, chain), see
+   miso_b200/csrc/philox.cuh and oracle/philox_ref.h.  Version 2 (default) runs
+   the 7 rounds that pass BigCrush, version 1 the 10 rounds of the first
+   release.  set = 1 | 2 selects (process-wide, before misob200_run), 0 only
+   queries; the environment variable MISOB200_STREAM=1 selects v1 at start-up.
+   Returns the version in force. */
+int misob200_stream_version(int set);
 
 /* host worker threads the library uses for the plan stage and the output
    epilogue: MISOB200_HOST_THREADS, else usable cores (affinity, cgroup quota)

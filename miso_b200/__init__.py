@@ -4,7 +4,7 @@ Host code is Python over a ctypes C ABI (include/miso_b200.h) over hand-written
 sm_100a CUDA (miso_b200/csrc/).  No CPU fallback: importing this package needs
 libmiso_b200.so, running anything needs a B200.
 """
-from ._lib import InternalError, LIB_PATH, device_count  # noqa: F401
+from ._lib import InternalError, LIB_PATH, device_count, stream_version  # noqa: F401
 from .batch import (Gene, Plan, ReadBatch, make_params, decode_summary,  # noqa: F401
                     MISO_START_AUTO, MISO_START_UNIFORM, MISO_START_RANDOM,
                     MISO_START_GIVEN, MISO_START_LINEAR, MISO_STOP_FIXEDNO,

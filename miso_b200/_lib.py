@@ -108,7 +108,7 @@ EXPORTS = [
     "misob200_release_device", "misob200_summarize", "misob200_bucket_timing", "misob200_compare",
     "misob200_transfer_bytes", "misob200_comm_unique_id",
     "misob200_comm_init", "misob200_comm_allgather", "misob200_comm_allgather_summaries",
-    "misob200_comm_allgather_compare", "misob200_host_threads",
+    "misob200_comm_allgather_compare", "misob200_host_threads", "misob200_stream_version",
     "misob200_plan_info_all", "misob200_plan_offsets_all", "misob200_write_miso_files", "misob200_format_fixed", "misob200_plan_write_miso", "misob200_comm_barrier_max",
     "misob200_comm_destroy", "misob200_host_alloc", "misob200_host_free",
 ]
@@ -127,6 +127,11 @@ def check(rc):
 
 def ptr(a):
     return None if a is None else a.ctypes.data
+
+
+def stream_version(set=0):
+    """Random-stream version in force (2: Philox4x32-7, default; 1: Philox4x32-10); set=1|2 selects."""
+    return int(lib.misob200_stream_version(int(set)))
 
 
 def device_count():

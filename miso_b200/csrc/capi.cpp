@@ -16,6 +16,7 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
              int32_t *status);
 int release_device(Plan &plan);
 int release_pool();
+int stream_version(int set);
 int summarize(Plan &plan, double *summary);
 int run_timing(Plan &plan, double *timing_ms);
 int device_count(int *n);
@@ -249,6 +250,7 @@ int misob200_compare(misob200_plan_t *plan_a, misob200_plan_t *plan_b, double *o
   return compare(plan_a->p, plan_b->p, out);
 }
 int misob200_host_threads(void) { return host_threads(); }
+int misob200_stream_version(int set) { return stream_version(set); }
 int misob200_summarize(misob200_plan_t *plan, double *summary) {
   if (!plan || !summary) return MISOB200_EINVAL;
   return summarize(plan->p, summary);

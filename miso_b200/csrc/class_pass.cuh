@@ -202,7 +202,7 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
 #pragma unroll (MODE == 0 ? (K >= kUnroll1FromK ? 1 : kUnrollCount) : kUnrollScore)
   for (int s = 0; s < nsteps; s++) {
     uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) (lane + 32 * s), 0u, gene, chain, key, x);
+    philox4x32(Q0 + (uint32_t) (lane + 32 * s), 0u, gene, chain, key, x);
     const uint32_t ids = __byte_perm(TM::ld(a), TM::ld(a + 4), sel);
     a += 128;
     uint32_t uc01 = 0, uc23 = 0;                      // MODE 1: the 4 reads' own codes
@@ -317,7 +317,7 @@ __device__ __noinline__ void class_literal(typename TileMem<SMEM>::addr_t rows, 
   for (int s = 0; s < nsteps; s++) {
     const int T = lane + 32 * s;
     uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
+    philox4x32(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
 #pragma unroll 1
     for (int i = 0; i < 4; i++) {
       const int rank = 4 * T - o + i;

@@ -69,7 +69,7 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
   for (int s = 0; s < nsteps; s++) {
     const int T = lane + 32 * s;
     uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
+    philox4x32(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
     uint32_t cw[K + 1], cx[WIDE ? K : 1];
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -161,7 +161,7 @@ __device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t row
   for (int s = 0; s < nsteps; s++) {
     const int T = lane + 32 * s;
     uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
+    philox4x32(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
 #pragma unroll 1
     for (int i = 0; i < 4; i++) {
       const int rank = 4 * T - o + i;

@@ -155,7 +155,7 @@ __device__ __forceinline__ void quad_pass(uint32_t a0, uint32_t a_end, int my_st
 #pragma unroll (MODE == 0 ? kUnrollCount : kUnrollScore)
   for (int s = 0; s < nsteps; s++) {
     uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) (mi + 8 * s), 0u, gene, chain, key, x);
+    philox4x32(Q0 + (uint32_t) (mi + 8 * s), 0u, gene, chain, key, x);
     const uint32_t aa = a < a_end ? a : a_end;
     const uint32_t ids = __byte_perm(TileMem<true>::ld(aa), TileMem<true>::ld(aa + 4), sel);
     a += 32;
@@ -247,7 +247,7 @@ __device__ __noinline__ void quad_literal(unsigned gmask, uint32_t rows, const u
   for (int s = 0; s < nsteps; s++) {
     const int T = mi + 8 * s;
     uint32_t x[4];
-    philox4x32_10(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
+    philox4x32(Q0 + (uint32_t) T, 0u, gene, chain, key, x);
 #pragma unroll 1
     for (int i = 0; i < 4; i++) {
       const int rank = 4 * T - o + i;

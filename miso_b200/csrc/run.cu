@@ -39,6 +39,18 @@ const char *last_error() { return g_error.c_str(); }
 
 constexpr int kBuckets = 2 * (kMaxIso + 1);
 
+// Stream version: 2 (Philox4x32-7, default) or 1 (Philox4x32-10, round 1's stream).
+static int g_stream_version = 0;
+int stream_version(int set) {
+  if (set == 1 || set == 2) g_stream_version = set;
+  if (!g_stream_version) {
+    const char *e = std::getenv("MISOB200_STREAM");
+    g_stream_version = (e && std::atoi(e) == 1) ? 1 : 2;
+  }
+  return g_stream_version;
+}
+static int stream_rounds() { return stream_version(0) == 1 ? 10 : 7; }
+
 int host_threads() {
   static int cached = 0;
   if (cached) return cached;
@@ -548,7 +560,7 @@ static int prepare_bucket(Plan &plan, DevState *st, Launch *out) {
   P.queue = st->d_queue + b;
   P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
   P.start = st->params.start;
-  P.key = philox_expand_key(st->params.seed);
+  P.key = philox_expand_key(st->params.seed, stream_rounds());
   P.slot_bytes = slot;
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;
@@ -622,7 +634,7 @@ static int prepare_quad(Plan &plan, DevState *st, Launch *out, int *rc) {
   P.queue = st->d_queue + b;
   P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
   P.start = st->params.start;
-  P.key = philox_expand_key(st->params.seed);
+  P.key = philox_expand_key(st->params.seed, stream_rounds());
   P.slot_bytes = slot;
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;

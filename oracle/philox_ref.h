@@ -2,7 +2,8 @@
  * oracle/philox_ref.h -- TEST INFRASTRUCTURE ONLY (never linked into the product).
  *
  * Plain-C statement of the random stream the whole repo agrees on
- * ("miso-b200 stream v1").  The reference never seeds its generator
+ * ("miso-b200 stream", v1 = Philox4x32-10, v2 = Philox4x32-7; phx_rounds below,
+ * set through refh_set_stream / mo_set_stream; the product's default is v2).  The reference never seeds its generator
  * (the only RNG hook is the vtable
  * splicing_rng_type_t, /root/reference/pysplicing/include/splicing_random.h:23-36),
  * so "same seed" is *defined* here and injected into the unmodified reference
@@ -10,7 +11,8 @@
  * oracle/miso_oracle.c; the CUDA product implements the same map in
  * miso_b200/csrc/philox.cuh.
  *
- *   generator : Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11)
+ *   generator : Philox4x32-R (Salmon, Moraes, Dror, Shaw, SC'11), R = phx_rounds:
+ *               10 (stream v1) or 7 (stream v2, the fewest rounds that pass BigCrush)
  *   key       : (seed & 0xffffffff, seed >> 32)
  *   counter   : (block, tag, gene_id, chain_id)    tag 0 = uniforms, 1 = normals
  *   uniform n : word (n & 3) of block (n >> 2), tag 0   ->  (w + 0.5) * 2^-32
@@ -37,12 +39,14 @@
 #define PHX_W0 0x9E3779B9u
 #define PHX_W1 0xBB67AE85u
 
+static int phx_rounds = 7;	/* stream v2; 10 = stream v1 */
+
 static inline void phx_4x32_10(const uint32_t ctr[4], const uint32_t key[2],
                                uint32_t out[4]) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
   uint32_t k0 = key[0], k1 = key[1];
   int r;
-  for (r = 0; r < 10; r++) {
+  for (r = 0; r < phx_rounds; r++) {
     uint64_t p0 = (uint64_t) PHX_M0 * c0;
     uint64_t p1 = (uint64_t) PHX_M1 * c2;
     uint32_t n0 = (uint32_t) (p1 >> 32) ^ c1 ^ k0;

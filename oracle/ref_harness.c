@@ -69,6 +69,13 @@ static splicing_rng_type_t refh_rngtype = {
 static splicing_rng_t refh_saved_default;
 static int refh_have_saved = 0;
 
+/* stream version: 1 = Philox4x32-10, 2 = Philox4x32-7 (philox_ref.h) */
+int refh_set_stream(int version) {
+  if (version == 1) phx_rounds = 10;
+  if (version == 2) phx_rounds = 7;
+  return phx_rounds == 10 ? 1 : 2;
+}
+
 /* rng_mode 0: Philox stream keyed (seed, gene, chain).
    rng_mode 1: the reference's own MT19937 default, seeded with `seed'
                (its fastest configuration; used for CPU-baseline timing). */

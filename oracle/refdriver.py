@@ -64,9 +64,18 @@ class RefOracle:
     PortOracle below shares every method except the simulators."""
     kind = "reference"
 
-    def __init__(self, path=REF_SO, prefix="refh_"):
+    def __init__(self, path=REF_SO, prefix="refh_", stream=None):
         self.lib = _Prefixed(C.CDLL(path), prefix)
         self.lib.refh_init()
+        # the Philox stream the oracle is driven by (rng_mode 0): version 2 = 7 rounds (the
+        # product's default), 1 = 10 rounds; MISOB200_STREAM follows the product's switch
+        if stream is None:
+            stream = 1 if os.environ.get("MISOB200_STREAM") == "1" else 2
+        self.set_stream(stream)
+
+    def set_stream(self, version):
+        self.stream = int(self.lib.refh_set_stream(int(version)))
+        return self.stream
 
     # -- setup stage ---------------------------------------------------
     def gene_info(self, exons, isoforms):
@@ -237,8 +246,8 @@ class PortOracle(RefOracle):
     """kind == "port": oracle/miso_oracle.c, the plain-C restatement."""
     kind = "port"
 
-    def __init__(self, path=PORT_SO):
-        RefOracle.__init__(self, path, "mo_")
+    def __init__(self, path=PORT_SO, stream=None):
+        RefOracle.__init__(self, path, "mo_", stream)
 
     def simulate_se(self, *a, **k):
         raise NotImplementedError("simulators exist only in oracle/_ref")

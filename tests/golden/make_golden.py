@@ -2,10 +2,11 @@
 container only: needs /root/reference for the SAM fixture and oracle/_ref, the
 UNMODIFIED reference C core, as the source of truth).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [1|2]      (stream version; default: both)
 
 Every case stores its inputs (gene structure, read positions, CIGARs) and the
-outputs of the reference driven by the miso-b200 stream v1 (oracle/philox_ref.h)
+outputs of the reference driven by the miso-b200 stream (oracle/philox_ref.h; golden_v1.npz:
+stream v1 = Philox4x32-10, golden_v2.npz: stream v2 = Philox4x32-7, the product's default)
 with the framework's chain convention: chain c of gene g owns stream
 (seed, g, c); the oracle is called once per chain with noChains=1 and the
 columns are interleaved s*C + c (tests/helpers.py:oracle_gene).
@@ -58,8 +59,9 @@ def skip_gene(K):
     return ex, iso
 
 
-def main():
-    ref = refdriver.RefOracle()
+def main(version):
+    ref = refdriver.RefOracle(stream=version)
+    assert ref.stream == version
     cases = {}
 
     ex, iso, pos, cig = cfg1_reads()
@@ -122,9 +124,11 @@ def main():
         out[pre + "accrej"] = np.asarray([want["accepted"], want["rejected"]], np.int64)
         out[pre + "class_templates"] = want["class_templates"]
         out[pre + "class_counts"] = want["class_counts"]
-    np.savez_compressed(os.path.join(HERE, "golden_v1.npz"), **out)
-    print("wrote", os.path.join(HERE, "golden_v1.npz"), os.path.getsize(os.path.join(HERE, "golden_v1.npz")), "bytes")
+    path = os.path.join(HERE, "golden_v%d.npz" % version)
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    for v in ([int(sys.argv[1])] if len(sys.argv) > 1 else [1, 2]):
+        main(v)

@@ -1,22 +1,29 @@
-"""Loader of tests/golden/golden_v1.npz (written by tests/golden/make_golden.py)."""
+"""Loader of tests/golden/golden_v<stream>.npz (written by tests/golden/make_golden.py): v1 = the
+reference driven by Philox4x32-10, v2 = by Philox4x32-7 (the product's default stream)."""
 import os
 
 import numpy as np
 
-PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+DEFAULT_STREAM = 1 if os.environ.get("MISOB200_STREAM") == "1" else 2
+STREAMS = (1, 2)
+
+
+def golden_path(version):
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v%d.npz" % version)
 
 
 class Case:
     pass
 
 
-def load_cases():
-    z = np.load(PATH)
+def load_cases(version=DEFAULT_STREAM):
+    z = np.load(golden_path(version))
     names = sorted({k.split("/")[0] for k in z.files})
     cases = []
     for name in names:
         c = Case()
         c.name = name
+        c.stream = version
         g = lambda f: z[name + "/" + f]   # noqa: E731
         c.exons = tuple((int(a), int(b)) for a, b in g("exons"))
         iso, cur = [], []

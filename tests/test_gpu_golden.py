@@ -4,10 +4,23 @@ pysplicing.MISO / MISOPaired, the batched plan API, and the .miso writer."""
 import numpy as np
 import pytest
 
-from golden_util import load_cases
+from golden_util import STREAMS, load_cases
 
 pytestmark = pytest.mark.gpu
-CASES = load_cases()
+CASES = [c for v in STREAMS for c in load_cases(v)]       # both stream versions (Philox4x32-10 / -7)
+IDS = ["v%d-%s" % (c.stream, c.name) for c in CASES]
+
+
+@pytest.fixture(autouse=True)
+def stream_of_the_case(request):
+    """Select the product's random-stream version the golden case was generated with."""
+    import miso_b200
+    case = request.node.callspec.params.get("case") if hasattr(request.node, "callspec") else None
+    was = miso_b200.stream_version()
+    if case is not None:
+        miso_b200.stream_version(case.stream)
+    yield
+    miso_b200.stream_version(was)
 
 
 @pytest.fixture(scope="module")
@@ -38,7 +51,7 @@ def chains_per_warp(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
+@pytest.mark.parametrize("case", CASES, ids=IDS)
 def test_pysplicing_entry_points_match_reference_golden(mb, case, chains_per_warp):
     import pysplicing
     gene = pysplicing.createGene(case.exons, case.isoforms)
@@ -71,7 +84,7 @@ def test_pysplicing_entry_points_match_reference_golden(mb, case, chains_per_war
 
 def test_sampler_front_end_writes_reference_format(mb, tmp_path):
     from miso_b200 import sampler, miso_format
-    case = [c for c in CASES if c.name == "cfg1_default"][0]
+    case = [c for c in load_cases() if c.name == "cfg1_default"][0]      # the default stream's golden
     parts = [sampler.Part("up", *case.exons[0]), sampler.Part("se", *case.exons[1]), sampler.Part("dn", *case.exons[2])]
     gene = sampler.GeneModel("ev1", parts, [["up", "se", "dn"], ["up", "dn"]], chrom="chr10", strand="+")
     prm = sampler.get_single_end_sampler_params(2, 36)

@@ -5,14 +5,17 @@ different libm build)."""
 import numpy as np
 import pytest
 
-from golden_util import Params, load_cases
+from golden_util import Params, STREAMS, load_cases
 from helpers import oracle_gene
 
-CASES = load_cases()
+CASES = [c for v in STREAMS for c in load_cases(v)]       # both stream versions (Philox4x32-10 / -7)
 
 
-@pytest.mark.parametrize("case", CASES, ids=[c.name for c in CASES])
-def test_port_reproduces_reference_golden(port, case):
+@pytest.mark.parametrize("case", CASES, ids=["v%d-%s" % (c.stream, c.name) for c in CASES])
+def test_port_reproduces_reference_golden(port, case, request):
+    was = port.stream
+    request.addfinalizer(lambda: port.set_stream(was))
+    port.set_stream(case.stream)
     got = oracle_gene(port, (case.exons, case.isoforms, case.pos, case.cig), bool(case.paired), Params(case),
                       case.gene_id, pe=case.pe, read_len=case.read_len, overhang=case.overhang)
     S = (case.n_iters - case.burn_in) // case.lag
@@ -26,7 +29,7 @@ def test_port_reproduces_reference_golden(port, case):
 
 
 def test_golden_covers_baseline_config_1():
-    c = [c for c in CASES if c.name == "cfg1_default"][0]
+    c = [c for c in CASES if c.name == "cfg1_default"][-1]
     assert len(c.pos) > 700 and len(c.isoforms) == 2 and c.n_chains == 6
     # the skipped exon of this event is mostly excluded in the C2C12 sample
     assert 0.03 < c.samples[0].mean() < 0.12

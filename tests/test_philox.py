@@ -4,6 +4,7 @@ import ctypes as C
 import math
 
 import numpy as np
+import pytest
 
 KAT = [  # counter, key, expected
     ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
@@ -21,10 +22,35 @@ def philox(lib, ctr, key):
     return tuple(o)
 
 
-def test_philox_known_answers(port):
+def philox_py(ctr, key, rounds):
+    """Philox4x32-R straight from the paper (Salmon et al. SC'11, fig. 2 + the Weyl key schedule)."""
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(rounds):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = (p1 >> 32) ^ c1 ^ k0, p1 & 0xffffffff, (p0 >> 32) ^ c3 ^ k1, p0 & 0xffffffff
+        k0, k1 = (k0 + 0x9E3779B9) & 0xffffffff, (k1 + 0xBB67AE85) & 0xffffffff
+    return (c0, c1, c2, c3)
+
+
+@pytest.fixture
+def stream(port, request):
+    """Select the oracle's stream version for one test, restore afterwards."""
+    was = port.stream
+    request.addfinalizer(lambda: port.set_stream(was))
+    return port.set_stream
+
+
+def test_philox_known_answers(port, stream):
     lib = port.lib._lib
+    stream(1)                                   # stream v1 = Philox4x32-10: Random123's vectors
     for ctr, key, want in KAT:
-        assert philox(lib, ctr, key) == want
+        assert philox(lib, ctr, key) == want == philox_py(ctr, key, 10)
+    stream(2)                                   # stream v2 = Philox4x32-7
+    rng = np.random.default_rng(0)
+    for ctr, key, _ in KAT + [(tuple(int(x) for x in rng.integers(0, 2 ** 32, 4)),
+                               tuple(int(x) for x in rng.integers(0, 2 ** 32, 2)), None) for _ in range(50)]:
+        assert philox(lib, ctr, key) == philox_py(ctr, key, 7) != philox_py(ctr, key, 10)
 
 
 def test_uniform_and_normal_maps(port):
