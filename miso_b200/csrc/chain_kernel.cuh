@@ -102,7 +102,7 @@ __device__ __forceinline__ void ring_push(unsigned *ring, unsigned *tail, unsign
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ring + q), "r"(unit) : "memory");
 }
 
-struct ChainParams {
+template <int ROUNDS> struct ChainParamsT {
   const GeneDesc *desc;
   const int *items;          // gene indices of this K bucket, longest first
   int n_genes;               // entries in items
@@ -122,7 +122,7 @@ struct ChainParams {
   int *accrej;               // [gene][chain][2]
   unsigned *queue;           // work counter
   int n_iters, burn_in, lag, start;
-  PhiloxKey key;
+  PhiloxKeyT<ROUNDS> key;     // stream v2: 7 rounds, v1: 10 (philox.cuh)
   int slot_bytes;            // shared-memory bytes per warp for a tile (0: stream tiles from L2)
   // class format only
   const double *neglog;      // neglog[n] = -log(n), n < n_neglog (read scores, miso_paired.c:409-411)
@@ -136,6 +136,7 @@ struct ChainParams {
   unsigned *ring;            // this bucket's ready queue: n_units * (n_seg - 1) slots, all kRingEmpty at launch
   unsigned *ring_tail;       // pushes so far
 };
+using ChainParams = ChainParamsT<7>;      // what run.cu fills: every ChainParamsT<R> has this layout
 
 }  // namespace misob200
 
@@ -250,8 +251,8 @@ __device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb) {
   return count_dot_body<K>(cnt_k, v_k, gb);
 }
 
-template <int K, bool SMEM, bool WIDE, int FMT>
-__device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_index, int chain,
+template <int K, bool SMEM, bool WIDE, int FMT, int ROUNDS>
+__device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int gene_index, int chain,
                           typename TileMem<SMEM>::addr_t rows, uint32_t ptab_s, const ClassRef &cr,
                           int m_begin, int m_end) {
   constexpr int len = K - 1;
@@ -272,7 +273,7 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
   for (int k = 0; k < K; k++) g_always[k] = FMT == 1 ? d.g_always[k] : 0;
   int thr_state = 0;       // class format: 0 thresholds stale (psi changed), 1 valid, 2 declined for this psi
   const uint32_t gid = d.gene_id;
-  const PhiloxKey &key = P.key;
+  const PhiloxKeyT<ROUNDS> &key = P.key;
   const int *L = d.L;
 
   ChainState *const st = P.state + ((long long) gene_index * P.n_chains + chain);
@@ -507,8 +508,8 @@ __device__ void run_chain(const ChainParams &P, const GeneDesc &d, int gene_inde
 #define MISOB200_CLASS_WARPS 16      /* A/B builds: 20 (96 registers) with MISOB200_PASS_NOINLINE */
 #endif
 constexpr int kClassWarps = MISOB200_CLASS_WARPS;
-template <int K, int WARPS, bool SMEM, bool WIDE, int FMT>
-__global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? 1 : (K <= 6 ? 4 : 3))) chain_kernel(const __grid_constant__ ChainParams P) {
+template <int K, int WARPS, bool SMEM, bool WIDE, int FMT, int ROUNDS>
+__global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? 1 : (K <= 6 ? 4 : 3))) chain_kernel(const __grid_constant__ ChainParamsT<ROUNDS> P) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *s_ptab = reinterpret_cast<double *>(smem);

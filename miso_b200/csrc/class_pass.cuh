@@ -173,10 +173,10 @@ __device__ __forceinline__ double neg_log_lp(int lp, const double *__restrict__ 
 //   MODE 1, 2: + the read score of the chosen isoforms (paired-end, miso_paired.c:157-163);
 //           runs before an iteration that records a sample (the MH ratio does not need
 //           the read score, the recorded log score does).
-template <int K, int MODE, bool SMEM, bool WIDE>
+template <int K, int MODE, bool SMEM, bool WIDE, class KEY>
 __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
                                                 uint32_t ptab_s, unsigned long long n_u, int R2, uint32_t gene,
-                                                uint32_t chain, const PhiloxKey &key,
+                                                uint32_t chain, const KEY &key,
                                                 const int *__restrict__ g_always,
                                                 const double *__restrict__ neglog, int n_neglog,
                                                 int (&cnt)[K], double &rp) {
@@ -263,19 +263,19 @@ __device__ __forceinline__ void class_pass_body(typename TileMem<SMEM>::addr_t r
 #else
 #define MISOB200_PASS_INLINE __forceinline__
 #endif
-template <int K, bool SMEM>
+template <int K, bool SMEM, class KEY>
 __device__ MISOB200_PASS_INLINE void class_pass(typename TileMem<SMEM>::addr_t rows, const ClassRef &cr,
                                            unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
-                                           const PhiloxKey &key, const int *__restrict__ g_always, int (&cnt)[K]) {
+                                           const KEY &key, const int *__restrict__ g_always, int (&cnt)[K]) {
   double unused;
   class_pass_body<K, 0, SMEM, false>(rows, 0, cr, 0u, n_u, R2, gene, chain, key, g_always, nullptr, 0, cnt, unused);
 }
 
 // MODE 1 out of line: one pass in `lag` runs it
-template <int K, bool SMEM, bool WIDE>
+template <int K, bool SMEM, bool WIDE, class KEY>
 __device__ __noinline__ void class_pass_rp(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
                                            uint32_t ptab_s, unsigned long long n_u, int R2, uint32_t gene,
-                                           uint32_t chain, const PhiloxKey &key, const int *__restrict__ g_always,
+                                           uint32_t chain, const KEY &key, const int *__restrict__ g_always,
                                            const double *__restrict__ neglog, int n_neglog, bool lp_safe, int *cnt_k,
                                            double *rp) {
   int cnt[K];
@@ -296,10 +296,10 @@ __device__ __noinline__ void class_pass_rp(typename TileMem<SMEM>::addr_t rows, 
 // Codes are rebuilt from the class record (uniform-code classes: the read's own code
 // wherever the record is non-zero).  Used for the final pass of chain 0 (emits the
 // per-read assignment, miso.c:943-946) and for passes thr_update declined.
-template <int K, bool SMEM, bool WIDE>
+template <int K, bool SMEM, bool WIDE, class KEY>
 __device__ __noinline__ void class_literal(typename TileMem<SMEM>::addr_t rows, int ucode_off, const ClassRef &cr,
                                            uint32_t ptab_s, double psi_k, unsigned long long n_u, int R2,
-                                           uint32_t gene, uint32_t chain, const PhiloxKey &key, int paired,
+                                           uint32_t gene, uint32_t chain, const KEY &key, int paired,
                                            const int *__restrict__ L, const double *__restrict__ neglog,
                                            int n_neglog, int *cnt_k, double *rp, uint8_t *__restrict__ ass_out) {
   using TM = TileMem<SMEM>;

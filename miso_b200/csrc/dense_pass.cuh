@@ -42,11 +42,11 @@ constexpr int kReadUnroll = MISOB200_READ_UNROLL;   // reads of a lane's step un
 // otherwise runs reassign_literal below instead.
 //   MODE 0: counts only.  MODE 1: + read score of the chosen isoform
 //   (miso_paired.c:157-163), needed when the next iteration records.
-template <int K, int MODE, bool SMEM, bool WIDE>
+template <int K, int MODE, bool SMEM, bool WIDE, class KEY>
 __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t rows, int row_bytes, int flag_off,
                                               uint32_t ptab_s, const double (&psi)[K],
                                               unsigned long long n_u, int R2, uint32_t gene,
-                                              uint32_t chain, const PhiloxKey &key, int paired,
+                                              uint32_t chain, const KEY &key, int paired,
                                               const int *__restrict__ L, int (&cnt)[K], double &rp) {
   using TM = TileMem<SMEM>;
   const int lane = threadIdx.x & 31;
@@ -140,10 +140,10 @@ __device__ __forceinline__ void reassign_pass(typename TileMem<SMEM>::addr_t row
 // per-read assignment, miso.c:943-946) and for passes the fast rule declined.
 // Not inlined and not unrolled over reads: it runs once or twice per chain.
 // psi_k is lane k's psi; returns lane k's count in cnt_k and the read score.
-template <int K, bool SMEM, bool WIDE>
+template <int K, bool SMEM, bool WIDE, class KEY>
 __device__ __noinline__ void reassign_literal(typename TileMem<SMEM>::addr_t rows, int row_bytes, int flag_off,
                                               uint32_t ptab_s, double psi_k, unsigned long long n_u,
-                                              int R2, uint32_t gene, uint32_t chain, const PhiloxKey &key,
+                                              int R2, uint32_t gene, uint32_t chain, const KEY &key,
                                               int paired, const int *__restrict__ L, int *cnt_k,
                                               double *rp, uint8_t *__restrict__ ass_out) {
   using TM = TileMem<SMEM>;

@@ -27,12 +27,18 @@ namespace misob200 {
 // run (the key is the seed), so the host expands them once and they travel in
 // the kernel parameter block: on the device they are constant-bank operands of
 // the round's XOR, not instructions.
-struct PhiloxKey { uint32_t k0[10], k1[10]; uint32_t rounds, pad_; };
-constexpr int kPhiloxMinRounds = 7;
+// The round count is a compile-time property of the key type, hence of every kernel: the two
+// stream versions are separate instantiations and only the selected one is ever resident in
+// the instruction caches (a run-time branch around three extra rounds at every call site cost
+// more in instruction fetch than the rounds it skipped).
+template <int R> struct PhiloxKeyT {
+  static constexpr int kRounds = R;
+  uint32_t k0[10], k1[10];
+};
+using PhiloxKey = PhiloxKeyT<7>;       // layout of every PhiloxKeyT<R>
 
-inline PhiloxKey philox_expand_key(uint64_t seed, int rounds) {
+inline PhiloxKey philox_expand_key(uint64_t seed) {
   PhiloxKey k;
-  k.rounds = (uint32_t) rounds; k.pad_ = 0;
   uint32_t a = (uint32_t) seed, b = (uint32_t) (seed >> 32);
   for (int r = 0; r < 10; r++) {
     k.k0[r] = a; k.k1[r] = b;
@@ -50,16 +56,11 @@ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_
   c1 = (uint32_t) p1; c3 = (uint32_t) p0;
   c0 = n0; c2 = n2;
 }
-// key.rounds is 7 (stream v2) or 10 (v1): seven rounds unconditionally, the other three behind one
-// warp-uniform branch on a kernel parameter
+template <class KEY>
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                           const PhiloxKey &key, uint32_t (&out)[4]) {
+                                           const KEY &key, uint32_t (&out)[4]) {
 #pragma unroll
-  for (int r = 0; r < kPhiloxMinRounds; r++) philox_round(c0, c1, c2, c3, key.k0[r], key.k1[r]);
-  if (key.rounds > (uint32_t) kPhiloxMinRounds) {
-#pragma unroll
-    for (int r = kPhiloxMinRounds; r < 10; r++) philox_round(c0, c1, c2, c3, key.k0[r], key.k1[r]);
-  }
+  for (int r = 0; r < KEY::kRounds; r++) philox_round(c0, c1, c2, c3, key.k0[r], key.k1[r]);
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
@@ -68,8 +69,9 @@ __device__ __forceinline__ double uniform_from_word(uint32_t w) {
   return __fma_rn((double) w, 0x1p-32, 0x1p-33);   // one instruction; exact either way
 }
 
+template <class KEY>
 __device__ __forceinline__ double stream_uniform(unsigned long long n, uint32_t gene, uint32_t chain,
-                                                 const PhiloxKey &key) {
+                                                 const KEY &key) {
   uint32_t x[4];
   philox4x32((uint32_t) (n >> 2), 0u, gene, chain, key, x);
   const uint32_t sel = (uint32_t) n & 3u;
@@ -77,8 +79,9 @@ __device__ __forceinline__ double stream_uniform(unsigned long long n, uint32_t 
   return uniform_from_word(w);
 }
 
+template <class KEY>
 __device__ __noinline__ double stream_normal(uint32_t n, uint32_t gene, uint32_t chain,
-                                                const PhiloxKey &key) {
+                                                const KEY &key) {
   uint32_t x[4];
   philox4x32(n, 1u, gene, chain, key, x);
   const unsigned long long a = ((unsigned long long) x[0] << 21) | (x[1] >> 11);

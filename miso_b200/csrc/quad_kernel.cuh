@@ -126,12 +126,12 @@ __device__ __forceinline__ uint32_t quad_thr_update(bool need, const ClassRef &c
 // (literal rule instead) passes a0 = a_end.
 //   MODE 0: counts.  MODE 1: + read score of the chosen isoforms (miso_paired.c:157-163),
 //   uniform codes from global memory.
-template <int K, int MODE, bool WIDE>
+template <int K, int MODE, bool WIDE, class KEY>
 __device__ __forceinline__ void quad_pass(uint32_t a0, uint32_t a_end, int my_steps,
                                           const unsigned char *__restrict__ ucode, int row_last,
                                           const ClassRef &cr, const double *__restrict__ ptab,
                                           unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
-                                          const PhiloxKey &key, const int (&g_always)[K],
+                                          const KEY &key, const int (&g_always)[K],
                                           const double *__restrict__ neglog, int n_neglog, int (&cnt)[K],
                                           double &rp) {
   constexpr int NT = Thr<K>::NT, TSA = Thr<K>::TSA, TSB = Thr<K>::TSB;
@@ -210,11 +210,11 @@ __device__ __forceinline__ void quad_pass(uint32_t a0, uint32_t a_end, int my_st
   if (MODE == 1) rp = group_sum(rp_lane);
 }
 
-template <int K, bool WIDE>
+template <int K, bool WIDE, class KEY>
 __device__ __noinline__ void quad_pass_rp(uint32_t a0, uint32_t a_end, int my_steps, const unsigned char *__restrict__ ucode,
                                           int row_last, const ClassRef &cr, const double *__restrict__ ptab,
                                           unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
-                                          const PhiloxKey &key, const int (&g_always)[K],
+                                          const KEY &key, const int (&g_always)[K],
                                           const double *__restrict__ neglog, int n_neglog, int *cnt_k, double *rp) {
   int cnt[K];
   quad_pass<K, 1, WIDE>(a0, a_end, my_steps, ucode, row_last, cr, ptab, n_u, R2, gene, chain, key, g_always, neglog,
@@ -227,11 +227,11 @@ __device__ __noinline__ void quad_pass_rp(uint32_t a0, uint32_t a_end, int my_st
 
 // ---- the literal rule of miso.c:59-83 for ONE group (class_literal, eight lanes) -----
 // Runs under divergence: only the lanes of `gmask` are here.
-template <int K, bool WIDE>
+template <int K, bool WIDE, class KEY>
 __device__ __noinline__ void quad_literal(unsigned gmask, uint32_t rows, const unsigned char *__restrict__ ucode,
                                           const ClassRef &cr, const double *__restrict__ ptab, double psi_k,
                                           unsigned long long n_u, int R2, uint32_t gene, uint32_t chain,
-                                          const PhiloxKey &key, int paired, const double *__restrict__ neglog,
+                                          const KEY &key, int paired, const double *__restrict__ neglog,
                                           int n_neglog, int *cnt_k, double *rp, uint8_t *__restrict__ ass_out) {
   const int lane = threadIdx.x & 31, mi = lane & 7, gb = lane & 24;
   const int o = (int) (n_u & 3ull);
@@ -311,8 +311,8 @@ __device__ __noinline__ void quad_literal(unsigned gmask, uint32_t rows, const u
 // ---- the kernel ---------------------------------------------------------------------
 // Shared memory per warp: [mbarrier 16 B | 4 x slot (core tile) | 4 x {L_k 32 B, threshold planes}].
 // slot_bytes is 32 mod 128, so the four groups' id words of one step sit in different banks.
-template <int K, int WARPS, bool WIDE>
-__global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_constant__ ChainParams P) {
+template <int K, int WARPS, bool WIDE, int ROUNDS>
+__global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_constant__ ChainParamsT<ROUNDS> P) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int len = K - 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
   unsigned char *slot = wbase + 16 + grp * P.slot_bytes;
   unsigned char *thr = wbase + 16 + kQuad * P.slot_bytes + grp * P.thr_bytes;
   const double *__restrict__ ptab = P.ptab;
-  const PhiloxKey &key = P.key;
+  const PhiloxKeyT<ROUNDS> &key = P.key;
 
   if (lane == 0) { mbar_init(bar, kQuad); fence_mbar_init(); }
   __syncwarp();

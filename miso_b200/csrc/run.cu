@@ -527,8 +527,13 @@ static int prepare_bucket(Plan &plan, DevState *st, Launch *out) {
     slot = FMT == 1 ? cls : 0;
     smem = (size_t) ptab_bytes + WARPS * (16 + (size_t) slot + thr);
   }
-  auto kern = plan.wide ? (in_smem ? chain_kernel<K, WARPS, true, true, FMT> : chain_kernel<K, WARPS, false, true, FMT>)
-                        : (in_smem ? chain_kernel<K, WARPS, true, false, FMT> : chain_kernel<K, WARPS, false, false, FMT>);
+  // (the two stream versions are separate kernels with identical parameter layout, philox.cuh)
+  const bool v1 = stream_rounds() == 10;
+  typedef void (*kern_t)(ChainParams);
+#define MISOB200_PICK(SM, WD) (v1 ? (kern_t) (void *) chain_kernel<K, WARPS, SM, WD, FMT, 10> : (kern_t) (void *) chain_kernel<K, WARPS, SM, WD, FMT, 7>)
+  kern_t kern = plan.wide ? (in_smem ? MISOB200_PICK(true, true) : MISOB200_PICK(false, true))
+                          : (in_smem ? MISOB200_PICK(true, false) : MISOB200_PICK(false, false));
+#undef MISOB200_PICK
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   {
     // the seven K buckets run as concurrent kernels: give them all the same L1/shared split
@@ -560,7 +565,7 @@ static int prepare_bucket(Plan &plan, DevState *st, Launch *out) {
   P.queue = st->d_queue + b;
   P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
   P.start = st->params.start;
-  P.key = philox_expand_key(st->params.seed, stream_rounds());
+  P.key = philox_expand_key(st->params.seed);
   P.slot_bytes = slot;
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;
@@ -604,7 +609,10 @@ static int prepare_quad(Plan &plan, DevState *st, Launch *out, int *rc) {
   const int slot = ((core + 127) & ~127) + 32;     // 32 mod 128: the four groups' id words fall in different banks
   const size_t smem = (size_t) WARPS * (16 + (size_t) kQuad * (slot + thr));
   if (smem > 227 * 1024) return 0;
-  auto kern = plan.wide ? quad_kernel<K, WARPS, true> : quad_kernel<K, WARPS, false>;
+  const bool v1 = stream_rounds() == 10;
+  typedef void (*kern_t)(ChainParams);
+  kern_t kern = plan.wide ? (v1 ? (kern_t) (void *) quad_kernel<K, WARPS, true, 10> : (kern_t) (void *) quad_kernel<K, WARPS, true, 7>)
+                          : (v1 ? (kern_t) (void *) quad_kernel<K, WARPS, false, 10> : (kern_t) (void *) quad_kernel<K, WARPS, false, 7>);
   *rc = MISOB200_ECUDA;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) {
     set_error(std::string("quad kernel: ") + cudaGetErrorString(cudaGetLastError()));
@@ -634,7 +642,7 @@ static int prepare_quad(Plan &plan, DevState *st, Launch *out, int *rc) {
   P.queue = st->d_queue + b;
   P.n_iters = st->params.n_iters; P.burn_in = st->params.burn_in; P.lag = st->params.lag;
   P.start = st->params.start;
-  P.key = philox_expand_key(st->params.seed, stream_rounds());
+  P.key = philox_expand_key(st->params.seed);
   P.slot_bytes = slot;
   P.neglog = st->d_neglog;
   P.n_neglog = st->n_neglog;

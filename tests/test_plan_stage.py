@@ -175,3 +175,33 @@ def test_odd_cigars_match_the_reference(ref_or_port):
     want = ref_or_port.match_pe(ex, iso, np.asarray(ppos, np.int32), pcig, 33, 80.0, 400.0, 4.0, 1)
     np.testing.assert_array_equal(np.where(codes > 0, codes - 1 + fs, -1), want["fraglen"])
     np.testing.assert_array_equal(order, want["order"])
+
+
+def test_synthetic_workload_has_the_read_mix_of_the_reference_simulator(ref):
+    """bench.py's generator (workloads/synth.cpp) against the reference's own paired-end simulator
+    (splicing_simulate_paired_reads, simulator.c:221-442, through oracle/_ref) on the same genes and
+    the same true psi: what sets the GPU's cost per gene -- the number of reads that draw (R2) and the
+    number of weight classes -- must agree within sampling noise."""
+    import miso_b200 as mb
+    from workloads import Workload
+    w = Workload(1, 60, 2000, 36, 250.0, 900.0, 4.0, seed=20260925)
+    ours = mb.Plan().append(w)
+    info = ours.info()
+    genes, poss, cigs = [], [], []
+    for g in range(60):
+        ex, isos, _, _ = w.gene(g)
+        K = len(isos)
+        pos, cig, _ = ref.simulate_pe(ex, isos, w.truth(g, K), 2000, 36, 250.0, 900.0, 4.0, seed=1000 + g)
+        genes.append(mb.Gene(ex, isos))
+        poss.append(pos)
+        cigs.append(cig)
+    theirs = mb.Plan().append(mb.ReadBatch(genes, poss, cigs, 36, 1, True, 250.0, 900.0, 4.0)).info()
+    assert (theirs[:, 0] == info[:, 0]).all() and (theirs[:, 1] == 2000).all() and (info[:, 1] == 2000).all()
+    for k in sorted(set(int(x) for x in info[:, 0])):
+        m = info[:, 0] == k
+        a, b = info[m, 2].mean(), theirs[m, 2].mean()
+        assert abs(a - b) <= 0.05 * max(a, b) + 6, (k, a, b)                       # drawing reads
+        assert abs(info[m, 3].mean() - theirs[m, 3].mean()) <= 1.5, k              # read classes (0/1 patterns)
+    # gene by gene: same psi, same structure -> R2 within binomial noise of each other
+    d = np.abs(info[:, 2] - theirs[:, 2])
+    assert np.median(d) <= 40 and d.max() <= 160, (np.median(d), d.max())
