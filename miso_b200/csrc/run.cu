@@ -483,14 +483,14 @@ struct Launch {
 };
 
 // Estimated whole-machine time of a bucket, ms per 5000 iterations and chain: the measured
-// bucket times of the cfg-3 benchmark (BENCH_r01, ~7.1k genes per isoform count: 24 (four chains
-// per warp) / 71 / 92 / 100 / 118 / 138 / 160 ms) scaled by the drawing reads of each gene
+// bucket times of the cfg-3 benchmark (profiles/r2_ab6_stream_v2_ct.log, ~7.1k genes per isoform
+// count: 26 (four chains per warp) / 64 / 82 / 91 / 108 / 132 / 153 ms) scaled by the drawing reads of each gene
 // -- the scalar part of an iteration costs about as much as the counting pass over 1000 reads
 // (profiles/r1_v8_single_K5_lines.txt).  Only the RATIOS between buckets matter: they set
 // each bucket's share of the SMs; helper grids absorb the error.
 static double bucket_work_ms(const Plan &plan, const std::vector<int> &v, int K, bool quad, bool dense) {
-  static const double ms_per_gene[kMaxIso + 1] = {0, 0, 24.3 / 7012, 70.6 / 7226, 91.7 / 7122, 100.4 / 7083,
-                                                  117.8 / 7168, 137.5 / 7166, 160.3 / 7223};
+  static const double ms_per_gene[kMaxIso + 1] = {0, 0, 25.9 / 7012, 63.5 / 7226, 81.8 / 7122, 91.3 / 7083,
+                                                  108.4 / 7168, 131.9 / 7166, 152.5 / 7223};
   static const double r2_ref[kMaxIso + 1] = {0, 0, 14, 973, 1415, 1557, 1620, 1672, 1708};
   double c = ms_per_gene[K];
   if (K == 2 && !quad) c *= 2.4;          // one chain per warp at K = 2: 64 vs 27 ms (r1_ab4)
@@ -797,7 +797,9 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
   const char *cl_env = std::getenv("MISOB200_CLUSTER");
   const int cluster = cl_env ? std::max(1, std::atoi(cl_env)) : 2;
   if (balanced) {
-    const long long slots = st->sm_count;
+    // shares are counted in clusters (TPCs): `slots` of them on the machine
+    const long long slots = st->sm_count / cluster;
+    auto need = [&](const Launch *L) { return (L->need_blocks + cluster - 1) / cluster; };
     double total = 0;
     for (auto *L : cls) total += L->work_ms;
     // water-filling: a bucket never gets more CTAs than it has units for; what it leaves goes to the rest
@@ -809,13 +811,13 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
       for (size_t i = 0; i < cls.size(); i++) {
         if (capped[i]) continue;
         const double want = open > 0 ? cls[i]->work_ms / open * free_slots : 0;
-        if ((double) cls[i]->need_blocks <= want) {
-          cls[i]->blocks = cls[i]->need_blocks; capped[i] = 1;
+        if ((double) need(cls[i]) <= want) {
+          cls[i]->blocks = need(cls[i]); capped[i] = 1;
           free_slots -= cls[i]->blocks; open -= cls[i]->work_ms; again = true;
         }
       }
     }
-    // largest-remainder rounding of the open buckets' shares, at least one SM each
+    // largest-remainder rounding of the open buckets' shares, at least one cluster each
     long long given = 0;
     std::vector<std::pair<double, size_t>> rem;
     for (size_t i = 0; i < cls.size(); i++)
@@ -827,18 +829,12 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
       }
     std::sort(rem.begin(), rem.end(), [](const std::pair<double, size_t> &a, const std::pair<double, size_t> &c) { return a.first > c.first; });
     for (size_t r = 0; r < rem.size() && given < free_slots; r++, given++) cls[rem[r].second]->blocks++;
-    if (cluster > 1) {      // whole clusters: round every share to a multiple, the largest bucket takes the difference
-      long long sum = 0;
-      Launch *big = cls[0];
-      for (auto *L : cls) {
-        L->blocks = std::max<long long>(cluster, (L->blocks + cluster / 2) / cluster * cluster);
-        sum += L->blocks;
-        if (L->work_ms > big->work_ms) big = L;
-      }
-      const long long usable = slots / cluster * cluster;
-      if (sum != usable && big->blocks + (usable - sum) >= cluster) big->blocks += usable - sum;
-    }
+    for (auto *L : cls) L->blocks *= cluster;
   }
+  if (std::getenv("MISOB200_SCHED_DEBUG"))
+    for (auto &L : Ls)
+      fprintf(stderr, "[sched] bucket %2d (K = %d%s): units %lld, work %.2f ms, need %lld CTAs, share %lld CTAs of %d warps\n", L.b,
+              L.b % (kMaxIso + 1), L.quad ? ", four chains per warp" : "", L.n_units, L.work_ms, L.need_blocks, L.blocks, L.warps);
   int prev = -1;
   for (auto &L : Ls) {
     const int b = L.b;
