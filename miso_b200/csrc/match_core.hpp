@@ -129,9 +129,9 @@ MISOB200_HD bool cigar_usable(const Cigar &cg, int read_len, int overhang) {
 // isoforms.  `position` / `cigar_off` point at the gene's first read.  col[k] receives the
 // code.  Returns 0 or MISOB200_EINVAL (unparsable CIGAR: the reference aborts the whole call,
 // solve.c:295-298; here the gene gets that status).
-template <class Code>
+template <class Code, class Off>
 MISOB200_HD int match_read(const IsoView &gv, const MatchParams &mp, const int32_t *position,
-                           const int64_t *cigar_off, const char *cigar, int r, Code *col) {
+                           const Off *cigar_off, const char *cigar, int r, Code *col) {
   const int K = gv.K;
   for (int k = 0; k < K; k++) col[k] = 0;
   Cigar cg;

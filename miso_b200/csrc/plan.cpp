@@ -15,6 +15,7 @@
 //     src/qsort.c through include/matrix.pmt:579-589).
 #include "plan.hpp"
 #include "match_core.hpp"
+#include "bm_sort.hpp"
 
 #include <algorithm>
 #include <array>
@@ -31,67 +32,6 @@
 namespace misob200 {
 
 namespace {
-
-// ---- Bentley-McIlroy index sort -----------------------------------------
-template <class Cmp>
-struct BMSort {
-  Cmp cmp;
-  static void swp(int32_t *v, long a, long b) { int32_t t = v[a]; v[a] = v[b]; v[b] = t; }
-  void insertion(int32_t *v, long n) {
-    for (long m = 1; m < n; m++)
-      for (long l = m; l > 0 && cmp(v[l - 1], v[l]) > 0; l--) swp(v, l, l - 1);
-  }
-  long med3(const int32_t *v, long a, long b, long c) {
-    if (cmp(v[a], v[b]) < 0) {
-      if (cmp(v[b], v[c]) < 0) return b;
-      return cmp(v[a], v[c]) < 0 ? c : a;
-    }
-    if (cmp(v[b], v[c]) > 0) return b;
-    return cmp(v[a], v[c]) < 0 ? a : c;
-  }
-  void sort(int32_t *v, long n) {
-    while (true) {
-      if (n < 7) { insertion(v, n); return; }
-      long mid = n / 2;
-      if (n > 7) {
-        long lo = 0, hi = n - 1;
-        if (n > 40) {
-          const long d = n / 8;
-          lo = med3(v, lo, lo + d, lo + 2 * d);
-          mid = med3(v, mid - d, mid, mid + d);
-          hi = med3(v, hi - 2 * d, hi - d, hi);
-        }
-        mid = med3(v, lo, mid, hi);
-      }
-      swp(v, 0, mid);                       // pivot parked at v[0]
-      long a = 1, b = 1, c = n - 1, d = n - 1;
-      bool moved = false;
-      while (true) {
-        int r;
-        while (b <= c && (r = cmp(v[b], v[0])) <= 0) {
-          if (r == 0) { moved = true; swp(v, a, b); a++; }
-          b++;
-        }
-        while (b <= c && (r = cmp(v[c], v[0])) >= 0) {
-          if (r == 0) { moved = true; swp(v, c, d); d--; }
-          c--;
-        }
-        if (b > c) break;
-        swp(v, b, c);
-        moved = true;
-        b++; c--;
-      }
-      if (!moved) { insertion(v, n); return; }
-      long r = a < b - a ? a : b - a;       // equal-to-pivot runs to the middle
-      for (long i = 0; i < r; i++) swp(v, i, b - r + i);
-      r = d - c < n - d - 1 ? d - c : n - d - 1;
-      for (long i = 0; i < r; i++) swp(v, b + i, n - r + i);
-      const long left = b - a, right = d - c;
-      if (left > 1) sort(v, left);
-      if (right > 1) { v += n - right; n = right; } else return;
-    }
-  }
-};
 
 struct ColCmp {           // include/matrix.pmt:546-561 on ptab[code]
   const int32_t *codes; const double *ptab; int K;
@@ -113,18 +53,6 @@ struct ProfT {
   void next(int s) { auto t = std::chrono::steady_clock::now(); g_prof[slot] += std::chrono::duration_cast<std::chrono::nanoseconds>(t - t0).count(); slot = s; t0 = t; }
   ~ProfT() { next(slot); }
 };
-// The same order from one integer comparison: every code is replaced by the dense rank of its
-// probability (equal probabilities -- the two tails of a symmetric insert model -- share a rank),
-// 16 bits per isoform, isoform 0 most significant.  BMSort sees exactly the comparison results
-// ColCmp would give, so the (unstable) tie order is unchanged.
-struct KeyCmp {
-  const unsigned __int128 *key;
-  int operator()(int32_t a, int32_t b) const {
-    const unsigned __int128 x = key[a], y = key[b];
-    return x < y ? -1 : (x > y ? 1 : 0);
-  }
-};
-
 struct GeneOut {
   GeneHost h;
   GeneDesc d;
@@ -168,8 +96,13 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   std::vector<int32_t> codes((size_t) K * (R > 0 ? R : 1), 0);
   if (pre) {
     if (pre->status[g]) { h.status = pre->status[g]; return; }
-    const uint16_t *src = pre->codes + pre->code_off[g];
-    for (size_t i = 0; i < (size_t) K * R; i++) codes[i] = src[i];
+    if (pre->codes8) {
+      const uint8_t *src = pre->codes8 + pre->code_off[g];
+      for (size_t i = 0; i < (size_t) K * R; i++) codes[i] = src[i];
+    } else {
+      const uint16_t *src = pre->codes16 + pre->code_off[g];
+      for (size_t i = 0; i < (size_t) K * R; i++) codes[i] = src[i];
+    }
   } else {
     const MatchParams mp{in.read_len, overhang, paired, plan.frag_start, plan.frag_len_n};
     for (int r = 0; r < R; r++)
@@ -183,6 +116,10 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   prof.next(1);
   // ---- draw order ---------------------------------------------------------
   std::vector<int32_t> order(R);
+  const int32_t *dev_order = (pre && pre->order && R > 0) ? pre->order + pre->pair_off[g] : nullptr;
+  if (dev_order && dev_order[0] >= 0) {      // sorted by order_kernel (match.cu): the same code, bm_sort.hpp
+    std::memcpy(order.data(), dev_order, (size_t) R * sizeof(int32_t));
+  } else {
   for (int r = 0; r < R; r++) order[r] = r;
   if ((int) plan.code_rank.size() == n_codes && !std::getenv("MISOB200_SORT_DOUBLES")) {
     std::vector<unsigned __int128> key(R > 0 ? R : 1);
@@ -191,11 +128,12 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
       for (int k = 0; k < K; k++) v = (v << 16) | plan.code_rank[codes[(size_t) r * K + k]];
       key[r] = v;
     }
-    BMSort<KeyCmp> sorter{KeyCmp{key.data()}};
+    BMSort<KeyCmp<unsigned __int128>> sorter{KeyCmp<unsigned __int128>{key.data()}};
     sorter.sort(order.data(), R);
   } else {
     BMSort<ColCmp> sorter{ColCmp{codes.data(), plan.ptab.data(), K}};
     sorter.sort(order.data(), R);
+  }
   }
 
   prof.next(2);
@@ -507,9 +445,13 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
   // optional: read <-> isoform compatibility on the GPU
   DeviceCodes dev_codes;
   const DeviceCodes *pre = nullptr;
+  std::unique_lock<std::mutex> device_lock;      // the staging buffers of match.cu are ours until the genes are built
   if (match_device >= 0) {
+    device_lock = std::unique_lock<std::mutex>(device_append_mutex());
     const MatchParams mp{in.read_len, in.overhang == 0 ? 1 : in.overhang, paired, plan.frag_start, plan.frag_len_n};
-    const int rc = match_on_device(in, mp, match_device, dev_codes);
+    static const std::vector<uint16_t> no_rank;
+    const int rc = match_on_device(in, mp, match_device, (int) plan.ptab.size(),
+                                   std::getenv("MISOB200_HOST_SORT") ? no_rank : plan.code_rank, dev_codes);
     if (rc) return rc;
     pre = &dev_codes;
   }

@@ -10,6 +10,7 @@
 // Paths are relative to /root/reference/pysplicing/.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -89,17 +90,23 @@ struct Plan {
   void *dev = nullptr;
 };
 
-// Compatibility codes computed by match.cu for a whole batch (u16: codes < kMaxCodes).
+// Compatibility codes and draw order computed by match.cu for a whole batch.  The arrays live in
+// pinned staging buffers owned by match.cu and stay valid until the next device append
+// (plan_append holds device_append_mutex() while it consumes them).
 struct MatchParams;
 struct DeviceCodes {
-  std::vector<uint16_t> codes_store;
-  std::vector<long long> code_off;       // per gene: offset of its K x R block (read-major, K contiguous)
+  std::vector<long long> code_off;       // per gene: offset of its R x K block (read-major, K contiguous)
+  std::vector<long long> pair_off;       // per gene: offset of its R order entries
   std::vector<int> status;               // per gene: 0 or MISOB200_EINVAL (unparsable CIGAR)
-  const uint16_t *codes = nullptr;
-  double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
+  const uint16_t *codes16 = nullptr;     // one of the two: 8-bit codes when the plan has at most 256 codes
+  const uint8_t *codes8 = nullptr;
+  const int32_t *order = nullptr;        // draw order (order[pair_off[g]] == -1: this gene is sorted on the host); may be null
+  double kernel_ms = 0, sort_ms = 0, h2d_ms = 0, d2h_ms = 0;
   long long bytes_in = 0, bytes_out = 0;
 };
-int match_on_device(const misob200_reads_t &reads, const MatchParams &mp, int device, DeviceCodes &out);
+int match_on_device(const misob200_reads_t &reads, const MatchParams &mp, int device, int n_codes,
+                    const std::vector<uint16_t> &code_rank, DeviceCodes &out);
+std::mutex &device_append_mutex();
 // timing of the last device matching of this thread's plan_append (ms; bytes)
 void last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, long long *bytes_in, long long *bytes_out);
 

@@ -1,6 +1,7 @@
-"""Read <-> isoform compatibility on the device (csrc/match.cu) against the
-host plan stage and the oracle: the same integer codes, draw order, classes, tiles and -- run
-through the chain kernels -- the same posteriors."""
+"""Read <-> isoform compatibility and the draw-order sort on the device (csrc/match.cu: match_kernel,
+order_kernel) against the host plan stage and the oracle: the same integer
+codes, draw order (the unstable quicksort's tie order included), classes, tiles and -- run through the
+chain kernels -- the same posteriors."""
 import numpy as np
 import pytest
 
@@ -43,7 +44,24 @@ def test_device_matching_equals_host_on_synthetic_batches(mb, kind, n_genes, rea
     dev = mb.Plan(keep_match=True).append(w, match_device=0)
     same_plan(mb, host, dev, n_genes)
     k_ms, h_ms, d_ms, b_in, b_out = mb.Plan.last_match_stats()
-    assert k_ms > 0 and b_in > 0 and b_out == 2 * int((host.info()[:, 0] * host.info()[:, 1]).sum())
+    info = host.info()
+    # one byte per code (at most 256 codes in this insert model) + four bytes of draw order per read
+    assert k_ms > 0 and b_in > 0 and b_out == int((info[:, 0] * info[:, 1]).sum()) + 4 * int(info[:, 1].sum())
+
+
+def test_device_order_with_wide_keys_and_long_genes(mb, monkeypatch):
+    """sd = 70: 561 fragment lengths -> 16-bit codes and more than 255 distinct probabilities, i.e. 128-bit
+    sort keys; a gene with 9000 pairs does not fit the sort kernel's shared-memory arrays and is ordered
+    by the host (same code, bm_sort.hpp); and the host-sort switch gives the same plan."""
+    w = mb.Workload(1, 40, 700, 36, 300.0, 4900.0, 4.0, seed=23)
+    host = mb.Plan(keep_match=True).append(w)
+    dev = mb.Plan(keep_match=True).append(w, match_device=0)
+    assert len(host.fragment_table()[0]) > 510
+    same_plan(mb, host, dev, 40)
+    big = mb.Workload(1, 3, 9000, 36, 250.0, 900.0, 4.0, seed=29)
+    same_plan(mb, mb.Plan(keep_match=True).append(big), mb.Plan(keep_match=True).append(big, match_device=0), 3, run=False)
+    monkeypatch.setenv("MISOB200_HOST_SORT", "1")
+    same_plan(mb, host, mb.Plan(keep_match=True).append(w, match_device=0), 40, run=False)
 
 
 def test_device_matching_on_odd_and_bad_cigars(mb, port):
