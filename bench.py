@@ -343,7 +343,8 @@ def setup_leg(mb, wl, ids, params, match_device, big_plan, big_out, barrier):
                          rundata=np.zeros((len(K), 9), np.int32), status=np.zeros(len(K), np.int32)))
     barrier(0.0)
     t0 = time.perf_counter()
-    res = run_pipelined(ws, params, outputs=outs, match_device=match_device)
+    stats = {}
+    res = run_pipelined(ws, params, outputs=outs, match_device=match_device, stats=stats)
     wall = barrier(time.perf_counter() - t0)
     for (plan, out), a in zip(res, bounds[:-1]):       # same posteriors as the one-plan run
         got, want = plan.gene_result(out, 0), big_plan.gene_result(big_out, int(a))
@@ -351,7 +352,7 @@ def setup_leg(mb, wl, ids, params, match_device, big_plan, big_out, barrier):
     for (plan, _), w in zip(res, ws):
         plan.close()
         w.close()
-    return wall, n_chunks
+    return wall, n_chunks, {k: [round(x, 4) for x in v] for k, v in stats.items()}
 
 
 def writer_leg(mb, plan, out, ids):
@@ -599,8 +600,8 @@ def main():
     timing = outs[0]["timing_ms"].copy()
     e2e_ms = 1e3 * wall_e2e / args.steps
 
-    setup_wall, setup_chunks = setup_leg(mb, wl, ids, params, md, plans[0], outs[0], barrier_max) \
-        if wl["samples"] == 1 else (t_plan + e2e_ms / 1e3, 1)
+    setup_wall, setup_chunks, setup_stats = setup_leg(mb, wl, ids, params, md, plans[0], outs[0], barrier_max) \
+        if wl["samples"] == 1 else (t_plan + e2e_ms / 1e3, 1, None)
 
     # what was timed, checked (untimed): the reference on a seeded sample of this very plan
     parity = None
@@ -637,6 +638,7 @@ def main():
                                        "classes, tile packing; %s) of batch i+1 overlaps the GPU run of batch i"
                                        % (setup_chunks, "matching on the GPU" if args.match_device else "host threads"),
                                "unpipelined_seconds": t_plan + e2e_ms / 1e3,
+                               "per_batch_seconds": setup_stats,
                                "plan_stage_s": t_plan, "host_threads": int(lib.misob200_host_threads())},
             "gpu_launches": int(launches),
             "gpu_launches_e2e": int(e2e_launches),

@@ -132,11 +132,24 @@ int misob200_plan_destroy(misob200_plan_t *plan);
 int misob200_plan_append(misob200_plan_t *plan, const misob200_reads_t *reads,
 			 int n_threads);
 /* the same, with the read <-> isoform compatibility (splicing_matchIso[_paired]
-   + splicing_parse_cigar, src/solve.c:8-306) computed by a kernel on `device`
+   + splicing_parse_cigar, src/solve.c:8-306) and the draw order
+   (splicing_order_matches, src/miso.c:988-993) computed by kernels on `device`
    instead of the host threads; identical plan, MISOB200_ECUDA without a GPU */
 int misob200_plan_append_device(misob200_plan_t *plan,
 				const misob200_reads_t *reads, int n_threads,
 				int device);
+/* the same in two calls, for pipelines with several batches in flight
+   (miso_b200/pipeline.py): _begin validates, fixes the plan's library and
+   ENQUEUES the batch's device work (copies in, match_kernel, order_kernel =
+   the draw-order sort of splicing_order_matches, src/miso.c:988-993, copies
+   out) on one of three internal stages; _finish waits for it and runs the host
+   half (read classes, tile packing).  `reads` and its arrays must stay alive
+   and unchanged in between.  Every _begin that returned 0 must be _finish-ed. */
+int misob200_plan_append_device_begin(misob200_plan_t *plan,
+				      const misob200_reads_t *reads,
+				      int device, void **pending);
+int misob200_plan_append_device_finish(misob200_plan_t *plan, void *pending,
+				       int n_threads);
 /* timing / traffic of the calling thread's last device matching:
    kernel, H2D, D2H in ms; input and output bytes */
 int misob200_last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms,

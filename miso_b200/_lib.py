@@ -63,6 +63,8 @@ def _load():
     lib.misob200_plan_gene_tile.argtypes = [vp, C.c_int32, vp, vp, vp]
     lib.misob200_plan_append.argtypes = [vp, vp, C.c_int]
     lib.misob200_plan_append_device.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.misob200_plan_append_device_begin.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    lib.misob200_plan_append_device_finish.argtypes = [vp, vp, C.c_int]
     lib.misob200_last_match_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.misob200_plan_size.argtypes = [vp, vp, vp, vp]
     lib.misob200_plan_gene_info.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
@@ -100,6 +102,7 @@ EXPORTS = [
     "misob200_version", "misob200_last_error", "misob200_init", "misob200_shutdown",
     "misob200_device_count", "misob200_plan_create", "misob200_plan_destroy",
     "misob200_plan_append", "misob200_plan_append_device", "misob200_last_match_stats",
+    "misob200_plan_append_device_begin", "misob200_plan_append_device_finish",
     "misob200_plan_keep_match", "misob200_plan_size",
     "misob200_plan_tile_format", "misob200_plan_gene_tile",
     "misob200_plan_gene_info", "misob200_plan_gene_classes", "misob200_plan_gene_match",

@@ -123,6 +123,23 @@ class Plan:
         self._info = None
         return self
 
+    def append_begin(self, reads, match_device=0):
+        """First half of a device append: enqueue the batch's GPU work (copies, match_kernel,
+        order_kernel) and return at once.  ``reads`` must stay alive until ``append_finish``."""
+        struct = reads.struct if hasattr(reads, "struct") else reads
+        pending = C.c_void_p()
+        check(lib.misob200_plan_append_device_begin(self.h, C.addressof(struct), int(match_device), C.byref(pending)))
+        self._pending = (pending, reads)
+        return self
+
+    def append_finish(self, n_threads=0):
+        """Second half: wait for the GPU work, then classes and tiles on the host threads."""
+        pending, _ = self._pending
+        self._pending = None
+        check(lib.misob200_plan_append_device_finish(self.h, pending, n_threads))
+        self._info = None
+        return self
+
     @staticmethod
     def last_match_stats():
         """(kernel ms, H2D ms, D2H ms, bytes in, bytes out) of the last device matching."""
@@ -134,6 +151,9 @@ class Plan:
 
     def close(self):
         if self.h:
+            if getattr(self, "_pending", None):      # a device append was begun and abandoned: release its stage
+                lib.misob200_plan_append_device_finish(self.h, self._pending[0], 0)
+                self._pending = None
             lib.misob200_plan_destroy(self.h)
             self.h = C.c_void_p()
 

@@ -79,6 +79,19 @@ int misob200_plan_append_device(misob200_plan_t *plan, const misob200_reads_t *r
   if (plan->p.dev) release_device(plan->p);
   return plan_append(plan->p, *reads, n_threads, device);
 }
+int misob200_plan_append_device_begin(misob200_plan_t *plan, const misob200_reads_t *reads, int device, void **pending) {
+  if (!plan || !reads || !pending) { set_error("plan_append_device_begin: null argument"); return MISOB200_EINVAL; }
+  if (device < 0) { set_error("plan_append_device_begin: device ordinal out of range"); return MISOB200_EINVAL; }
+  if (plan->p.dev) release_device(plan->p);
+  PendingAppend *p = nullptr;
+  const int rc = plan_append_device_begin(plan->p, *reads, device, &p);
+  *pending = p;
+  return rc;
+}
+int misob200_plan_append_device_finish(misob200_plan_t *plan, void *pending, int n_threads) {
+  if (!plan || !pending) { set_error("plan_append_device_finish: null argument"); return MISOB200_EINVAL; }
+  return plan_append_device_finish(plan->p, static_cast<PendingAppend *>(pending), n_threads);
+}
 int misob200_last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, int64_t *bytes_in, int64_t *bytes_out) {
   long long bi = 0, bo = 0;
   last_match_stats(kernel_ms, h2d_ms, d2h_ms, &bi, &bo);

@@ -23,6 +23,7 @@
 // Codes and order come back to pinned staging buffers; read classes and tile packing stay on the
 // host (plan.cpp).  All device and pinned buffers are grow-only and reused from call to call.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -137,7 +138,12 @@ __global__ void __launch_bounds__(32) order_kernel(const OrderArgs a) {
 }
 
 // ---- persistent buffers ------------------------------------------------------------------
-struct Pool {
+// kStages independent sets of device + pinned buffers, so that the batches of a pipeline can be in
+// different phases at once (miso_b200/pipeline.py): one being copied in, one in the kernels or
+// copying out, one being finished by the host threads.  A stage is acquired by stage_submit and
+// released by stage_release; submit blocks while all are taken.
+struct Stage {
+  bool busy = false;
   int device = -1;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[5] = {};
@@ -146,8 +152,10 @@ struct Pool {
   void *h[3] = {};                // pinned: 0 u32 CIGAR offsets (in), 1 codes (out), 2 order (out)
   size_t hcap[3] = {};
 };
+constexpr int kStages = 3;
 std::mutex g_mu;
-Pool g_pool;
+std::condition_variable g_cv;
+Stage g_stage[kStages];
 
 thread_local double t_kernel_ms = 0, t_h2d_ms = 0, t_d2h_ms = 0;
 thread_local long long t_bytes_in = 0, t_bytes_out = 0;
@@ -161,7 +169,7 @@ thread_local long long t_bytes_in = 0, t_bytes_out = 0;
     }                                                                                      \
   } while (0)
 
-int pool_device(Pool &p, int device) {
+int pool_device(Stage &p, int device) {
   MCK(cudaSetDevice(device));
   if (p.device == device) return 0;
   if (p.device >= 0) {            // a different GPU than last time: start over
@@ -178,7 +186,7 @@ int pool_device(Pool &p, int device) {
   for (auto &e : p.ev) MCK(cudaEventCreate(&e));
   return 0;
 }
-int pool_dev(Pool &p, int i, size_t bytes) {
+int pool_dev(Stage &p, int i, size_t bytes) {
   bytes = std::max<size_t>(bytes, 16);
   if (bytes <= p.cap[i]) return 0;
   cudaFree(p.d[i]); p.d[i] = nullptr; p.cap[i] = 0;
@@ -186,7 +194,7 @@ int pool_dev(Pool &p, int i, size_t bytes) {
   p.cap[i] = bytes + bytes / 8;
   return 0;
 }
-int pool_host(Pool &p, int i, size_t bytes) {
+int pool_host(Stage &p, int i, size_t bytes) {
   bytes = std::max<size_t>(bytes, 16);
   if (bytes <= p.hcap[i]) return 0;
   if (p.h[i]) cudaFreeHost(p.h[i]);
@@ -198,8 +206,6 @@ int pool_host(Pool &p, int i, size_t bytes) {
 
 }  // namespace
 
-std::mutex &device_append_mutex() { return g_mu; }
-
 void last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, long long *bytes_in, long long *bytes_out) {
   if (kernel_ms) *kernel_ms = t_kernel_ms;
   if (h2d_ms) *h2d_ms = t_h2d_ms;
@@ -208,9 +214,22 @@ void last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, long lo
   if (bytes_out) *bytes_out = t_bytes_out;
 }
 
-// code_rank: dense rank of ptab[code] (empty: no device sort, the host orders the reads)
-int match_on_device(const misob200_reads_t &in, const MatchParams &mp, int device, int n_codes,
-                    const std::vector<uint16_t> &code_rank, DeviceCodes &out) {
+void stage_release(int stage) {
+  if (stage < 0 || stage >= kStages) return;
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_stage[stage].busy = false;
+  }
+  g_cv.notify_all();
+}
+
+// Phase 1: copies in, kernels and copies out are ENQUEUED on the stage's stream; the call returns
+// when the pageable inputs have been handed to the driver.  code_rank: dense rank of ptab[code]
+// (empty: no device sort, the host orders the reads).  out.stage identifies the stage for
+// stage_wait / stage_release.
+int stage_submit(const misob200_reads_t &in, const MatchParams &mp, int device, int n_codes,
+                 const std::vector<uint16_t> &code_rank, DeviceCodes &out) {
+  out.stage = -1;
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
     cudaGetLastError();
@@ -248,7 +267,15 @@ int match_on_device(const misob200_reads_t &in, const MatchParams &mp, int devic
   for (uint16_t r : code_rank) max_rank = std::max<int>(max_rank, r);
   const bool key64 = max_rank < 256;
 
-  Pool &P = g_pool;                 // (the caller holds device_append_mutex())
+  int stage = -1;
+  {
+    std::unique_lock<std::mutex> lock(g_mu);
+    g_cv.wait(lock, [&] { for (int i = 0; i < kStages; i++) if (!g_stage[i].busy) { stage = i; return true; } return false; });
+    g_stage[stage].busy = true;
+  }
+  out.stage = stage;
+  Stage &P = g_stage[stage];
+  struct Guard { int s; bool armed; ~Guard() { if (armed) stage_release(s); } } guard{stage, true};
   if (int rc = pool_device(P, device)) return rc;
   // device buffers: 0-3 gene structure, 4 read_off, 5 position, 6 u32 CIGAR offsets, 7 CIGAR text, 8 code_off,
   // 9 codes, 10 per-gene status + two work counters, 11 pair_off + order + rank table
@@ -260,7 +287,7 @@ int match_on_device(const misob200_reads_t &in, const MatchParams &mp, int devic
   for (int i = 0; i < 12; i++) if (int rc = pool_dev(P, i, sz[i])) return rc;
   if (int rc = pool_host(P, 0, sz[6])) return rc;
   if (int rc = pool_host(P, 1, code_bytes)) return rc;
-  if (int rc = pool_host(P, 2, (size_t) std::max<long long>(n_pairs, 1) * 4)) return rc;
+  if (int rc = pool_host(P, 2, (size_t) std::max<long long>(n_pairs, 1) * 4 + (size_t) G * 4)) return rc;      // order, then status
 
   // 32-bit CIGAR offsets relative to the batch's text (half the bytes of the 64-bit ABI array), into pinned memory
   {
@@ -337,18 +364,32 @@ int match_on_device(const misob200_reads_t &in, const MatchParams &mp, int devic
   MCK(cudaEventRecord(P.ev[3], P.stream));
   MCK(cudaMemcpyAsync(P.h[1], P.d[9], std::max<size_t>(code_bytes, 1), cudaMemcpyDeviceToHost, P.stream));
   if (sorted) MCK(cudaMemcpyAsync(P.h[2], d_order, (size_t) n_pairs * 4, cudaMemcpyDeviceToHost, P.stream));
-  MCK(cudaMemcpyAsync(out.status.data(), d_status, (size_t) G * 4, cudaMemcpyDeviceToHost, P.stream));
+  // (status goes to pinned memory too: a pageable destination would make this call wait for the kernels)
+  out.n_pairs = n_pairs;
+  MCK(cudaMemcpyAsync(static_cast<char *>(P.h[2]) + (size_t) std::max<long long>(n_pairs, 1) * 4, d_status, (size_t) G * 4,
+                      cudaMemcpyDeviceToHost, P.stream));
   MCK(cudaEventRecord(P.ev[4], P.stream));
-  MCK(cudaStreamSynchronize(P.stream));
   if (narrow) out.codes8 = static_cast<const uint8_t *>(P.h[1]); else out.codes16 = static_cast<const uint16_t *>(P.h[1]);
   out.order = sorted ? static_cast<const int32_t *>(P.h[2]) : nullptr;
+  out.bytes_in = bytes_in;
+  out.bytes_out = (long long) code_bytes + (sorted ? n_pairs * 4 : 0);
+  guard.armed = false;
+  return 0;
+}
+
+// Phase 2: wait for the stage's copies and kernels; codes / order / status are then readable.
+int stage_wait(DeviceCodes &out) {
+  if (out.stage < 0 || out.stage >= kStages) { set_error("match stage: no batch in flight"); return MISOB200_EINVAL; }
+  Stage &P = g_stage[out.stage];
+  MCK(cudaSetDevice(P.device));
+  MCK(cudaStreamSynchronize(P.stream));
+  std::memcpy(out.status.data(), static_cast<char *>(P.h[2]) + (size_t) std::max<long long>(out.n_pairs, 1) * 4,
+              out.status.size() * sizeof(int));
   float ms = 0;
   cudaEventElapsedTime(&ms, P.ev[0], P.ev[1]); out.h2d_ms = ms;
   cudaEventElapsedTime(&ms, P.ev[1], P.ev[2]); out.kernel_ms = ms;
   cudaEventElapsedTime(&ms, P.ev[2], P.ev[3]); out.sort_ms = ms;
   cudaEventElapsedTime(&ms, P.ev[3], P.ev[4]); out.d2h_ms = ms;
-  out.bytes_in = bytes_in;
-  out.bytes_out = (long long) code_bytes + (sorted ? n_pairs * 4 : 0);
   t_kernel_ms = out.kernel_ms + out.sort_ms; t_h2d_ms = out.h2d_ms; t_d2h_ms = out.d2h_ms;
   t_bytes_in = out.bytes_in; t_bytes_out = out.bytes_out;
   return 0;

@@ -400,7 +400,8 @@ void fragment_table(Plan &plan) {
 
 }  // namespace
 
-int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match_device) {
+// Validation + the plan's library (fragment table, code ranks): what an append fixes before any read is looked at.
+static int prepare_library(Plan &plan, const misob200_reads_t &in) {
   if (in.n_genes < 0 || !in.iso_off || !in.exon_off || !in.read_off) {
     set_error("plan_append: null or negative input"); return MISOB200_EINVAL;
   }
@@ -425,7 +426,6 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
     set_error("plan_append: a plan holds one library (read length, overhang, insert model)");
     return MISOB200_EINVAL;
   }
-
   if (plan.code_rank.size() != plan.ptab.size()) {
     // dense rank of every code's probability (KeyCmp)
     const int n = (int) plan.ptab.size();
@@ -440,21 +440,12 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
     }
     if (n > 65535) plan.code_rank.clear();      // (never: kMaxCodes)
   }
+  return 0;
+}
 
+// the host half of an append: per-gene classes, constants and tiles on the worker threads, then the merge
+static int build_and_merge(Plan &plan, const misob200_reads_t &in, int n_threads, const DeviceCodes *pre) {
   const int G = in.n_genes;
-  // optional: read <-> isoform compatibility on the GPU
-  DeviceCodes dev_codes;
-  const DeviceCodes *pre = nullptr;
-  std::unique_lock<std::mutex> device_lock;      // the staging buffers of match.cu are ours until the genes are built
-  if (match_device >= 0) {
-    device_lock = std::unique_lock<std::mutex>(device_append_mutex());
-    const MatchParams mp{in.read_len, in.overhang == 0 ? 1 : in.overhang, paired, plan.frag_start, plan.frag_len_n};
-    static const std::vector<uint16_t> no_rank;
-    const int rc = match_on_device(in, mp, match_device, (int) plan.ptab.size(),
-                                   std::getenv("MISOB200_HOST_SORT") ? no_rank : plan.code_rank, dev_codes);
-    if (rc) return rc;
-    pre = &dev_codes;
-  }
   std::vector<GeneOut> outs(G);
   std::atomic<int> next(0);
   int nt = n_threads > 0 ? n_threads : host_threads();
@@ -490,6 +481,46 @@ int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match
     for (auto &x : g_prof) x = 0;
   }
   return 0;
+}
+
+struct PendingAppend {
+  DeviceCodes codes;
+  const misob200_reads_t *reads = nullptr;
+  misob200_reads_t copy{};          // the struct itself (pointers + scalars); the arrays stay the caller's
+};
+
+int plan_append_device_begin(Plan &plan, const misob200_reads_t &in, int device, PendingAppend **pending) {
+  if (!pending) return MISOB200_EINVAL;
+  *pending = nullptr;
+  if (int rc = prepare_library(plan, in)) return rc;
+  PendingAppend *p = new PendingAppend();
+  p->copy = in;
+  const MatchParams mp{in.read_len, in.overhang == 0 ? 1 : in.overhang, in.paired ? 1 : 0, plan.frag_start, plan.frag_len_n};
+  static const std::vector<uint16_t> no_rank;
+  const int rc = stage_submit(in, mp, device, (int) plan.ptab.size(),
+                              std::getenv("MISOB200_HOST_SORT") ? no_rank : plan.code_rank, p->codes);
+  if (rc) { delete p; return rc; }
+  *pending = p;
+  return 0;
+}
+
+int plan_append_device_finish(Plan &plan, PendingAppend *p, int n_threads) {
+  if (!p) { set_error("plan_append_device_finish: nothing pending"); return MISOB200_EINVAL; }
+  int rc = stage_wait(p->codes);
+  if (!rc) rc = build_and_merge(plan, p->copy, n_threads, &p->codes);
+  stage_release(p->codes.stage);
+  delete p;
+  return rc;
+}
+
+int plan_append(Plan &plan, const misob200_reads_t &in, int n_threads, int match_device) {
+  if (match_device >= 0) {      // optional: read <-> isoform compatibility and draw order on the GPU
+    PendingAppend *p = nullptr;
+    if (int rc = plan_append_device_begin(plan, in, match_device, &p)) return rc;
+    return plan_append_device_finish(plan, p, n_threads);
+  }
+  if (int rc = prepare_library(plan, in)) return rc;
+  return build_and_merge(plan, in, n_threads, nullptr);
 }
 
 }  // namespace misob200

@@ -91,8 +91,7 @@ struct Plan {
 };
 
 // Compatibility codes and draw order computed by match.cu for a whole batch.  The arrays live in
-// pinned staging buffers owned by match.cu and stay valid until the next device append
-// (plan_append holds device_append_mutex() while it consumes them).
+// the pinned staging buffers of one of match.cu's stages and stay valid until stage_release.
 struct MatchParams;
 struct DeviceCodes {
   std::vector<long long> code_off;       // per gene: offset of its R x K block (read-major, K contiguous)
@@ -101,18 +100,28 @@ struct DeviceCodes {
   const uint16_t *codes16 = nullptr;     // one of the two: 8-bit codes when the plan has at most 256 codes
   const uint8_t *codes8 = nullptr;
   const int32_t *order = nullptr;        // draw order (order[pair_off[g]] == -1: this gene is sorted on the host); may be null
+  int stage = -1;                        // match.cu stage holding the buffers
+  long long n_pairs = 0;
   double kernel_ms = 0, sort_ms = 0, h2d_ms = 0, d2h_ms = 0;
   long long bytes_in = 0, bytes_out = 0;
 };
-int match_on_device(const misob200_reads_t &reads, const MatchParams &mp, int device, int n_codes,
-                    const std::vector<uint16_t> &code_rank, DeviceCodes &out);
-std::mutex &device_append_mutex();
+int stage_submit(const misob200_reads_t &reads, const MatchParams &mp, int device, int n_codes,
+                 const std::vector<uint16_t> &code_rank, DeviceCodes &out);
+int stage_wait(DeviceCodes &out);
+void stage_release(int stage);
 // timing of the last device matching of this thread's plan_append (ms; bytes)
 void last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, long long *bytes_in, long long *bytes_out);
 
 void set_error(const std::string &msg);
 // match_device < 0: compatibility on the host; >= 0: on that GPU
 int plan_append(Plan &plan, const misob200_reads_t &reads, int n_threads, int match_device = -1);
+// the same in two calls, so that a pipeline can have several batches in flight: _begin validates,
+// fixes the plan's library and ENQUEUES the device work of the batch (copies in, match_kernel,
+// order_kernel, copies out); _finish waits for it and runs the host half (classes, tiles).
+// `reads` must stay alive and unchanged between the two calls.
+struct PendingAppend;
+int plan_append_device_begin(Plan &plan, const misob200_reads_t &reads, int device, PendingAppend **pending);
+int plan_append_device_finish(Plan &plan, PendingAppend *pending, int n_threads);
 
 // Host worker threads for the plan stage and the output epilogues: MISOB200_HOST_THREADS, else
 // the cores this process may use (affinity mask, cgroup cpu.max quota) divided by the ranks
