@@ -1,4 +1,7 @@
 // miso_b200/csrc/capi.cpp -- extern "C" entry points declared in include/miso_b200.h.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -240,12 +243,22 @@ int misob200_run(misob200_plan_t *plan, const misob200_params_t *params, double 
                  int32_t *assignment, int32_t *rundata, int32_t *status, double *timing_ms,
                  int32_t *launches) {
   if (!plan || !params) { set_error("run: null argument"); return MISOB200_EINVAL; }
+  const bool dbg = std::getenv("MISOB200_RUN_DEBUG") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t0 = now();
   if (int rc = upload(plan->p, *params)) return rc;
-  // posteriors of finished buckets travel to the host while later buckets run; download()
-  // then only fetches the assignments and counters
+  auto t1 = now();
+  // pinned output buffers are written by the kernels themselves; download() then only fetches
+  // the assignments and counters
   if (int rc = run_resident(plan->p, nullptr, launches, samples, loglik)) return rc;
+  auto t2 = now();
   if (int rc = download(plan->p, nullptr, nullptr, assignment, rundata, status)) return rc;
   run_timing(plan->p, timing_ms);
+  if (dbg) {
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[run] %zu genes: upload %.1f ms, run_resident %.1f ms (kernels %.1f), download + epilogue %.1f ms\n",
+            plan->p.desc.size(), ms(t0, t1), ms(t1, t2), timing_ms ? timing_ms[1] : 0.0, ms(t2, now()));
+  }
   return 0;
 }
 int misob200_bucket_timing(misob200_plan_t *plan, double *ms9) {

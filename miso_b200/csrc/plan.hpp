@@ -85,6 +85,7 @@ struct Plan {
   int lay_chains = -1;
   long long lay_S = -1, lay_n_samples = 0, lay_n_loglik = 0;
   size_t lay_genes = 0;
+  long long lay_generation = 0;          // bumped whenever the descriptors' output offsets are rewritten
   long long lay_range[2 * (kMaxIso + 1) + 1][4] = {};
   // device side (owned by run.cu)
   void *dev = nullptr;

@@ -109,7 +109,13 @@ struct DevState {
   cudaStream_t cstream = nullptr;          // device->host copies of finished buckets
   cudaEvent_t cdone = nullptr;
   bool uploaded = false, have_run = false;
-  bool pinned_tiles = false, pinned_desc = false;
+  // pinned staging of the plan's tile arena and descriptors (grow-only, pooled with the state): the
+  // plan's own arrays are pageable std::vectors, and page-locking them per plan (cudaHostRegister)
+  // cost 0.4 s per fresh plan while other threads of the process were allocating
+  uint8_t *h_stage = nullptr;
+  size_t cap_h_stage = 0;
+  bool tiles_staged = false;
+  long long staged_layout = -1;      // Plan.lay_generation of the descriptors in h_stage
   std::vector<double> h_ptab;       // plan.ptab + the 1.0 of the uniform-code classes
   std::vector<double> h_neglog;     // -log(n), read scores of the class format
   uint8_t *h_drawn = nullptr;       // pinned staging of the drawn assignments / accept counters (grow-only)
@@ -126,12 +132,13 @@ struct DevState {
   }
 };
 
-// Released device states of small plans, kept for the next plan on the same GPU: streams, events,
-// device buffers and pinned staging survive, so back-to-back pysplicing.MISO calls (one gene per
-// plan, the way misopy/run_miso.py drives the sampler) pay no allocation after the first.
+// Released device states, kept for the next plan on the same GPU: streams, events, device buffers
+// and pinned staging survive, so back-to-back pysplicing.MISO calls (one gene per plan, the way
+// misopy/run_miso.py drives the sampler) and the batches of a pipeline (miso_b200/pipeline.py)
+// pay no allocation after the first.
 static std::mutex g_pool_mu;
 static std::vector<DevState *> g_pool;
-constexpr size_t kPoolMaxStates = 4, kPoolMaxBytes = 64u << 20;
+constexpr size_t kPoolMaxStates = 4, kPoolMaxBytes = 4ull << 30;      // (device bytes held by the pool, all states together)
 
 template <class T>
 static int ensure_dev(T *&p, size_t &cap, size_t need_bytes) {
@@ -234,6 +241,7 @@ void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, l
     if (bucket_of(plan.desc[g]) < 0) place((int) g);
   range[2 * (kMaxIso + 1)][0] = s0; range[2 * (kMaxIso + 1)][1] = so; range[2 * (kMaxIso + 1)][2] = l0; range[2 * (kMaxIso + 1)][3] = lo;
   plan.lay_chains = p.n_chains; plan.lay_S = S; plan.lay_genes = plan.desc.size();
+  plan.lay_generation++;
   plan.lay_n_samples = so; plan.lay_n_loglik = lo;
   if (range_out) std::memcpy(range_out, plan.lay_range, sizeof(plan.lay_range));
   *n_samples = so; *n_loglik = lo;
@@ -254,6 +262,7 @@ static void free_dev(DevState *st) {
   for (auto &e : st->kend) if (e) cudaEventDestroy(e);
   if (st->h_drawn) cudaFreeHost(st->h_drawn);
   if (st->h_accrej) cudaFreeHost(st->h_accrej);
+  if (st->h_stage) cudaFreeHost(st->h_stage);
   for (auto &s : st->kstream) if (s) cudaStreamDestroy(s);
   if (st->stream) cudaStreamDestroy(st->stream);
   if (st->cstream) cudaStreamDestroy(st->cstream);
@@ -264,14 +273,16 @@ static void free_dev(DevState *st) {
 int release_device(Plan &plan) {
   DevState *st = static_cast<DevState *>(plan.dev);
   if (st) {
-    if (st->pinned_tiles) cudaHostUnregister(plan.tiles.data());
-    if (st->pinned_desc) cudaHostUnregister(plan.desc.data());
-    st->pinned_tiles = st->pinned_desc = false;
+    st->tiles_staged = false;
+  st->staged_layout = -1;
+    st->staged_layout = -1;
     st->uploaded = st->have_run = false;
     bool pooled = false;
-    if (st->device_bytes() <= kPoolMaxBytes) {
+    {
       std::lock_guard<std::mutex> lock(g_pool_mu);
-      if (g_pool.size() < kPoolMaxStates) { g_pool.push_back(st); pooled = true; }
+      size_t held = 0;
+      for (DevState *q : g_pool) held += q->device_bytes();
+      if (g_pool.size() < kPoolMaxStates && held + st->device_bytes() <= kPoolMaxBytes) { g_pool.push_back(st); pooled = true; }
     }
     if (!pooled) free_dev(st);
   }
@@ -319,9 +330,29 @@ int device_init(int device) {
 
 static int copy_inputs(Plan &plan, DevState *st) {
   const size_t G = plan.desc.size(), tile_bytes = plan.tiles.size();
+  // tiles (once per plan) and descriptors (the output layout may have changed) into pinned staging
+  const size_t tile_pad = (tile_bytes + 255) & ~(size_t) 255, desc_bytes = G * sizeof(GeneDesc);
+  if (int r = ensure_pinned(st->h_stage, st->cap_h_stage, tile_pad + desc_bytes)) return r;
+  if (!st->tiles_staged) {
+    const int nt = tile_bytes >= (8u << 20) ? std::max(1, std::min(host_threads(), 8)) : 1;
+    if (nt == 1) std::memcpy(st->h_stage, plan.tiles.data(), tile_bytes);
+    else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; t++) {
+        const size_t a = tile_bytes * t / nt, b = tile_bytes * (t + 1) / nt;
+        pool.emplace_back([=, &plan] { std::memcpy(st->h_stage + a, plan.tiles.data() + a, b - a); });
+      }
+      for (auto &t : pool) t.join();
+    }
+    st->tiles_staged = true;
+  }
+  if (G && st->staged_layout != plan.lay_generation) {
+    std::memcpy(st->h_stage + tile_pad, plan.desc.data(), desc_bytes);
+    st->staged_layout = plan.lay_generation;
+  }
   CK(cudaEventRecord(st->ev[0], st->stream));
-  if (tile_bytes) CK(cudaMemcpyAsync(st->d_tiles, plan.tiles.data(), tile_bytes, cudaMemcpyHostToDevice, st->stream));
-  if (G) CK(cudaMemcpyAsync(st->d_desc, plan.desc.data(), G * sizeof(GeneDesc), cudaMemcpyHostToDevice, st->stream));
+  if (tile_bytes) CK(cudaMemcpyAsync(st->d_tiles, st->h_stage, tile_bytes, cudaMemcpyHostToDevice, st->stream));
+  if (G) CK(cudaMemcpyAsync(st->d_desc, st->h_stage + tile_pad, desc_bytes, cudaMemcpyHostToDevice, st->stream));
   CK(cudaMemcpyAsync(st->d_ptab, st->h_ptab.data(), st->h_ptab.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
   CK(cudaMemcpyAsync(st->d_neglog, st->h_neglog.data(), st->h_neglog.size() * sizeof(double), cudaMemcpyHostToDevice, st->stream));
   for (int b = 0; b < kBuckets; b++)
@@ -432,12 +463,8 @@ int upload(Plan &plan, const misob200_params_t &p) {
   if (!st->d_queue) CK(cudaMalloc(&st->d_queue, kBuckets * sizeof(unsigned)));
   if (!st->d_ring_tail) CK(cudaMalloc(&st->d_ring_tail, kBuckets * sizeof(unsigned)));
 
-  // pin the plan's arenas once so the per-run H2D runs at link speed (small plans: not worth the call)
-  if (tile_bytes >= (1u << 20) && cudaHostRegister(plan.tiles.data(), tile_bytes, cudaHostRegisterDefault) == cudaSuccess)
-    st->pinned_tiles = true;
-  if (tile_bytes >= (1u << 20) && G && cudaHostRegister(plan.desc.data(), G * sizeof(GeneDesc), cudaHostRegisterDefault) == cudaSuccess)
-    st->pinned_desc = true;
-  cudaGetLastError();
+  st->tiles_staged = false;
+  st->staged_layout = -1;
   if (int r = ensure_pinned(st->h_drawn, st->cap_h_drawn, (size_t) plan.n_drawn)) return r;
   if (int r = ensure_pinned(st->h_accrej, st->cap_h_accrej, GC * 2 * sizeof(int))) return r;
   return copy_inputs(plan, st);

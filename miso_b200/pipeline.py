@@ -29,7 +29,8 @@ from .batch import Plan
 _END = object()
 
 
-def run_pipelined(read_batches, params, outputs=None, match_device=None, depth=2, on_result=None, stats=None):
+def run_pipelined(read_batches, params, outputs=None, match_device=None, depth=2, on_result=None, stats=None,
+                  release=True):
     """read_batches: iterable of objects ``Plan.append`` accepts (``ReadBatch``, a synthetic
     ``Workload`` ...), or of callables returning one (a batch can be loaded lazily by the first
     pipeline thread).  Every batch becomes its own plan, run as soon as it is planned.
@@ -38,6 +39,8 @@ def run_pipelined(read_batches, params, outputs=None, match_device=None, depth=2
     on_result(i, plan, out): called after batch i has run (e.g. to write its ``.miso`` files);
     the setup threads keep working meanwhile.  stats: optional dict, receives per-batch seconds
     (``plan``: setup threads busy, ``wait``: main thread waiting for a plan, ``run``: GPU run).
+    release: give a batch's device buffers back once it has run and on_result has seen it (its outputs
+    are in host memory by then; summaries / comparisons on the device need release=False).
     Returns the list of (plan, out).
     """
     t_plan, t_wait, t_run = [], [], []
@@ -112,6 +115,8 @@ def run_pipelined(read_batches, params, outputs=None, match_device=None, depth=2
             done.append((plan, out))
             if on_result is not None:
                 on_result(i, plan, out)
+            if release:
+                plan.release_device()       # the device state goes back to the library's pool: the next batch reuses it
     finally:
         stop.set()
         while any(t.is_alive() for t in threads):       # unblock threads waiting on a full queue
