@@ -149,7 +149,7 @@ struct Stage {
   cudaEvent_t ev[5] = {};
   void *d[12] = {};
   size_t cap[12] = {};
-  void *h[3] = {};                // pinned: 0 u32 CIGAR offsets (in), 1 codes (out), 2 order (out)
+  void *h[3] = {};                // pinned: 0 all inputs (CIGAR offsets as u32), 1 codes (out), 2 order + status (out)
   size_t hcap[3] = {};
 };
 constexpr int kStages = 3;
@@ -285,19 +285,39 @@ int stage_submit(const misob200_reads_t &in, const MatchParams &mp, int device, 
       (size_t) std::max<long long>(n_cig, 1), (size_t) (G + 1) * 8, code_bytes, (size_t) G * 4 + 8,
       (size_t) (G + 1) * 8 + (size_t) std::max<long long>(n_pairs, 1) * 4 + (size_t) std::max(n_codes, 1) * 2 + 64};
   for (int i = 0; i < 12; i++) if (int rc = pool_dev(P, i, sz[i])) return rc;
-  if (int rc = pool_host(P, 0, sz[6])) return rc;
+  // every input goes through ONE pinned staging buffer (offsets 256-byte aligned): the copies to the
+  // device are then truly asynchronous -- a pageable source makes cudaMemcpyAsync hold the calling
+  // thread (and, for hundreds of MB, other threads' CUDA calls) until the data has been staged
+  size_t in_off[11], in_total = 0;
+  const size_t in_sz[11] = {sz[0], sz[1], sz[2], sz[3], sz[4], sz[5], sz[6], sz[7], sz[8], (size_t) (G + 1) * 8,
+                            (size_t) std::max(n_codes, 1) * 2};
+  for (int i = 0; i < 11; i++) { in_off[i] = in_total; in_total += (in_sz[i] + 255) & ~(size_t) 255; }
+  if (int rc = pool_host(P, 0, in_total)) return rc;
   if (int rc = pool_host(P, 1, code_bytes)) return rc;
   if (int rc = pool_host(P, 2, (size_t) std::max<long long>(n_pairs, 1) * 4 + (size_t) G * 4)) return rc;      // order, then status
-
-  // 32-bit CIGAR offsets relative to the batch's text (half the bytes of the 64-bit ABI array), into pinned memory
+  unsigned char *hin = static_cast<unsigned char *>(P.h[0]);
   {
-    uint32_t *o32 = static_cast<uint32_t *>(P.h[0]);
-    const int nt = std::max(1, std::min(host_threads(), 16));
-    auto conv = [&](long long a, long long b) { for (long long i = a; i < b; i++) o32[i] = (uint32_t) (in.cigar_off[i] - cig0); };
-    if (n_reads < (1 << 20) || nt == 1) conv(0, n_reads + 1);
+    const void *small_src[11] = {in.iso_off, in.exon_off, in.exon_start, in.exon_end, in.read_off, nullptr, nullptr, nullptr,
+                                 out.code_off.data(), out.pair_off.data(), do_sort ? code_rank.data() : nullptr};
+    const size_t small_n[11] = {(size_t) (G + 1) * 4, (size_t) (n_iso + 1) * 4, (size_t) n_exon * 4, (size_t) n_exon * 4, (size_t) (G + 1) * 8,
+                                0, 0, 0, (size_t) (G + 1) * 8, (size_t) (G + 1) * 8, do_sort ? (size_t) n_codes * 2 : 0};
+    for (int i = 0; i < 11; i++) if (small_src[i] && small_n[i]) std::memcpy(hin + in_off[i], small_src[i], small_n[i]);
+    // the three big ones on the worker threads: positions, CIGAR text, and the CIGAR offsets as 32-bit
+    // offsets relative to the batch's text (half the bytes of the 64-bit ABI array)
+    uint32_t *o32 = reinterpret_cast<uint32_t *>(hin + in_off[6]);
+    const int nt = n_reads < (1 << 20) ? 1 : std::max(1, std::min(host_threads(), 8));
+    auto part = [&](int t) {
+      const long long a = (n_reads + 1) * t / nt, b = (n_reads + 1) * (t + 1) / nt;
+      for (long long i = a; i < b; i++) o32[i] = (uint32_t) (in.cigar_off[i] - cig0);
+      const long long pa = n_reads * t / nt, pb = n_reads * (t + 1) / nt;
+      if (pb > pa) std::memcpy(hin + in_off[5] + (size_t) pa * 4, in.position + pa, (size_t) (pb - pa) * 4);
+      const long long ca = n_cig * t / nt, cb = n_cig * (t + 1) / nt;
+      if (cb > ca) std::memcpy(hin + in_off[7] + (size_t) ca, in.cigar + cig0 + ca, (size_t) (cb - ca));
+    };
+    if (nt == 1) part(0);
     else {
       std::vector<std::thread> pool;
-      for (int t = 0; t < nt; t++) pool.emplace_back(conv, (n_reads + 1) * t / nt, (n_reads + 1) * (t + 1) / nt);
+      for (int t = 0; t < nt; t++) pool.emplace_back(part, t);
       for (auto &t : pool) t.join();
     }
   }
@@ -305,19 +325,17 @@ int stage_submit(const misob200_reads_t &in, const MatchParams &mp, int device, 
   unsigned *d_next = reinterpret_cast<unsigned *>(d_status + G);
   MCK(cudaMemsetAsync(d_status, 0, (size_t) G * 4 + 8, P.stream));
   MCK(cudaEventRecord(P.ev[0], P.stream));
-  const void *src[9] = {in.iso_off, in.exon_off, in.exon_start, in.exon_end, in.read_off, in.position, P.h[0],
-                        in.cigar + cig0, out.code_off.data()};
   long long bytes_in = 0;
   for (int i = 0; i < 9; i++) {
-    MCK(cudaMemcpyAsync(P.d[i], src[i], sz[i], cudaMemcpyHostToDevice, P.stream));
+    MCK(cudaMemcpyAsync(P.d[i], hin + in_off[i], sz[i], cudaMemcpyHostToDevice, P.stream));
     bytes_in += (long long) sz[i];
   }
   unsigned char *d11 = static_cast<unsigned char *>(P.d[11]);
   long long *d_pair_off = reinterpret_cast<long long *>(d11);
   int32_t *d_order = reinterpret_cast<int32_t *>(d11 + (size_t) (G + 1) * 8);
   uint16_t *d_rank = reinterpret_cast<uint16_t *>(d11 + (size_t) (G + 1) * 8 + (size_t) std::max<long long>(n_pairs, 1) * 4);
-  MCK(cudaMemcpyAsync(d_pair_off, out.pair_off.data(), (size_t) (G + 1) * 8, cudaMemcpyHostToDevice, P.stream));
-  if (do_sort) MCK(cudaMemcpyAsync(d_rank, code_rank.data(), (size_t) n_codes * 2, cudaMemcpyHostToDevice, P.stream));
+  MCK(cudaMemcpyAsync(d_pair_off, hin + in_off[9], (size_t) (G + 1) * 8, cudaMemcpyHostToDevice, P.stream));
+  if (do_sort) MCK(cudaMemcpyAsync(d_rank, hin + in_off[10], (size_t) n_codes * 2, cudaMemcpyHostToDevice, P.stream));
   MCK(cudaEventRecord(P.ev[1], P.stream));
 
   MatchArgs a;
