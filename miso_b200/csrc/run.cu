@@ -412,7 +412,7 @@ int upload(Plan &plan, const misob200_params_t &p) {
       CK(cudaStreamCreateWithPriority(&st->kstream[b], cudaStreamNonBlocking, prio_hi));
       CK(cudaStreamCreateWithPriority(&st->hstream[b], cudaStreamNonBlocking, prio_lo));
       CK(cudaEventCreateWithFlags(&st->kdone[b], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&st->kmain[b], cudaEventDisableTiming));
+      CK(cudaEventCreate(&st->kmain[b]));      // (timed: the calibration reads kbeg -> kmain)
       CK(cudaEventCreate(&st->kbeg[b]));
       CK(cudaEventCreate(&st->kend[b]));
     }
@@ -515,14 +515,25 @@ struct Launch {
 // -- the scalar part of an iteration costs about as much as the counting pass over 1000 reads
 // (profiles/r1_v8_single_K5_lines.txt).  Only the RATIOS between buckets matter: they set
 // each bucket's share of the SMs; helper grids absorb the error.
+// Self-calibration of that table: after every balanced step of some size the main grids' run times
+// say which buckets were given too few SMs (they end last); the per-(layout, K) correction factors
+// below follow them with a damped update, so the second step of a plan -- and the first step of the
+// next plan of the process, e.g. the next batch of a pipeline -- starts from measured ratios.
+static std::mutex g_cal_mu;
+static double g_cal[2][kMaxIso + 1] = {{1, 1, 1, 1, 1, 1, 1, 1, 1}, {1, 1, 1, 1, 1, 1, 1, 1, 1}};
+
 static double bucket_work_ms(const Plan &plan, const std::vector<int> &v, int K, bool quad, bool dense) {
   static const double ms_per_gene[kMaxIso + 1] = {0, 0, 25.9 / 7012, 63.5 / 7226, 81.8 / 7122, 91.3 / 7083,
                                                   108.4 / 7168, 131.9 / 7166, 152.5 / 7223};
   static const double r2_ref[kMaxIso + 1] = {0, 0, 14, 973, 1415, 1557, 1620, 1672, 1708};
   double c = ms_per_gene[K];
-  if (K == 2 && !quad) c *= 2.4;          // one chain per warp at K = 2: 64 vs 27 ms (r1_ab4)
-  if (K > 2 && quad) c *= 0.9;
+  if (K == 2 && !quad) c *= 2.1;          // one chain per warp at K = 2: 54 vs 26 ms (r2_ab5)
+  if (K > 2 && quad) c *= (K == 3 ? 0.75 : K == 4 ? 0.85 : K == 5 ? 0.93 : 1.05);      // r2_ab8_quad_fair.log
   if (dense) c *= 2.0;
+  else {
+    std::lock_guard<std::mutex> lock(g_cal_mu);
+    c *= g_cal[quad ? 1 : 0][K];
+  }
   double w = 0;
   for (int g : v) w += c * (1000.0 + plan.desc[g].R2) / (1000.0 + r2_ref[K]);
   return w;
@@ -627,10 +638,13 @@ static int prepare_quad(Plan &plan, DevState *st, Launch *out, int *rc) {
     for (int g : v) r2 += plan.desc[g].R2;
     const char *lim = std::getenv("MISOB200_QUAD_MAX_READS");
     const char *cpw = std::getenv("MISOB200_CHAINS_PER_WARP");      // "4": tests force the layout
-    // (K = 2 has the cheapest counting pass -- one threshold per read -- so the scalar part weighs
-    // more at a given read count: cfg-2, 750 drawing reads, runs 1.6x faster four to a warp; at
-    // K = 3 and ~1000 reads the two layouts are level once the single layout is cut into segments)
-    const long long max_mean = lim ? std::atoll(lim) : (cpw && std::atoi(cpw) == 4) ? (1LL << 40) : (K == 2 ? 1200 : 850);
+    // With the machine kept full either way (28 000 events of one isoform count, profiles/r2_ab8_quad_fair.log)
+    // four chains per warp win up to K = 5 at the 1000-1600 drawing reads of cfg-3 -- K = 3: 193 vs 257 ms,
+    // K = 5: 351 vs 379 ms -- and lose from K = 7 (525 vs 500 ms): the scalar part they save shrinks relative
+    // to the counting pass as K and the read count grow.  (Round 1 measured the layouts bucket by bucket,
+    // where a bucket of four-chain units is a single wave and pays its full latency; under the balanced
+    // policy every bucket has several waves on its own SM share.)
+    const long long max_mean = lim ? std::atoll(lim) : (cpw && std::atoi(cpw) == 4) ? (1LL << 40) : (K == 2 ? 2500 : K <= 5 ? 2000 : 850);
     if (!v.empty() && r2 > max_mean * (long long) v.size()) return 0;
   }
   const int slot = ((core + 127) & ~127) + 32;     // 32 mod 128: the four groups' id words fall in different banks
@@ -791,6 +805,29 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
     const char *cpw = std::getenv("MISOB200_CHAINS_PER_WARP");
     if (cpw) quad = std::atoi(cpw) == 4;
   }
+  // A four-chain unit takes ~4x as long as one chain, so a bucket of them has a quarter of the
+  // waves: four chains per warp only where the bucket still gets >= 2.5 waves on its SM share
+  // (waves = step time / unit latency; with fewer, the bucket's own latency sets the step: a rank's
+  // 6 250-event shard ran 137 instead of 87 ms with K = 4, 5 four to a warp).  K = 2 units are short.
+  bool quad_ok[kMaxIso + 1];
+  {
+    const bool forced = std::getenv("MISOB200_CHAINS_PER_WARP") || std::getenv("MISOB200_QUAD_MAX_READS");
+    const double resident_warps = 16.0 * st->sm_count;
+    double total = 0, work[kMaxIso + 1] = {0};
+    for (int fmt = 0; fmt < 2; fmt++)
+      for (int k = 2; k <= kMaxIso; k++) {
+        const auto &v = st->items[fmt * (kMaxIso + 1) + k];
+        if (v.empty()) continue;
+        const double w = bucket_work_ms(plan, v, k, k == 2 && fmt == 1, fmt == 0);
+        total += w;
+        if (fmt == 1) work[k] = w;
+      }
+    for (int k = 2; k <= kMaxIso; k++) {
+      const size_t n = st->items[(kMaxIso + 1) + k].size();
+      const double unit_ms = n ? 4.0 * work[k] * resident_warps / (double) n : 0.0;      // latency of a four-chain unit
+      quad_ok[k] = forced || k == 2 || (unit_ms > 0 && total / unit_ms >= 2.5);
+    }
+  }
   // dense buckets first (slowest per read), big K before small K (longest chains)
   std::vector<Launch> Ls;
   for (int fmt = 0; fmt < 2 && !rc; fmt++)
@@ -799,7 +836,7 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
       if (st->items[b].empty()) continue;
       if (only_k && k != only_k) continue;
       Launch L;
-      if (!(fmt && quad && prepare_quad_k(plan, st, k, &L, &rc))) rc = fmt ? prepare_k<1>(plan, st, k, &L) : prepare_k<0>(plan, st, k, &L);
+      if (!(fmt && quad && quad_ok[k] && prepare_quad_k(plan, st, k, &L, &rc))) rc = fmt ? prepare_k<1>(plan, st, k, &L) : prepare_k<0>(plan, st, k, &L);
       if (rc) return rc;
       Ls.push_back(L);
     }
@@ -860,8 +897,9 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
   }
   if (std::getenv("MISOB200_SCHED_DEBUG"))
     for (auto &L : Ls)
-      fprintf(stderr, "[sched] bucket %2d (K = %d%s): units %lld, work %.2f ms, need %lld CTAs, share %lld CTAs of %d warps\n", L.b,
-              L.b % (kMaxIso + 1), L.quad ? ", four chains per warp" : "", L.n_units, L.work_ms, L.need_blocks, L.blocks, L.warps);
+      fprintf(stderr, "[sched] bucket %2d (K = %d%s): units %lld, work %.2f ms (calibration %.3f), need %lld CTAs, share %lld CTAs of %d warps\n", L.b,
+              L.b % (kMaxIso + 1), L.quad ? ", four chains per warp" : "", L.n_units, L.work_ms, g_cal[L.quad ? 1 : 0][L.b % (kMaxIso + 1)],
+              L.need_blocks, L.blocks, L.warps);
   int prev = -1;
   for (auto &L : Ls) {
     const int b = L.b;
@@ -953,6 +991,28 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
 #endif
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, st->ev[2], st->ev[3]));
+  if (balanced && ms >= 20.0f && !std::getenv("MISOB200_NO_CALIBRATION")) {
+    // measured work of a bucket ~ run time of its main grid x its SMs; compare the buckets' shares of
+    // that with their shares of the estimate (only buckets with several waves: the others are latency)
+    double sum_m = 0, sum_w = 0;
+    std::vector<double> m(cls.size(), 0.0);
+    for (size_t i = 0; i < cls.size(); i++) {
+      float t = 0;
+      if (cls[i]->n_units < 2 * cls[i]->blocks * cls[i]->warps) { m[i] = -1; continue; }
+      if (cudaEventElapsedTime(&t, st->kbeg[cls[i]->b], st->kmain[cls[i]->b]) != cudaSuccess) { cudaGetLastError(); m[i] = -1; continue; }
+      m[i] = (double) t * (double) cls[i]->blocks;
+      sum_m += m[i]; sum_w += cls[i]->work_ms;
+    }
+    if (sum_m > 0 && sum_w > 0) {
+      std::lock_guard<std::mutex> lock(g_cal_mu);
+      for (size_t i = 0; i < cls.size(); i++) {
+        if (m[i] <= 0) continue;
+        const double r = (m[i] / sum_m) / (cls[i]->work_ms / sum_w);
+        double &c = g_cal[cls[i]->quad ? 1 : 0][cls[i]->b % (kMaxIso + 1)];
+        c = std::min(4.0, std::max(0.25, c * std::pow(std::min(2.0, std::max(0.5, r)), 0.7)));
+      }
+    }
+  }
   if (kernel_ms) *kernel_ms = ms;
   if (launches) *launches = nl;
   st->have_run = true;

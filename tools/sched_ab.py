@@ -28,7 +28,7 @@ for n in sizes:
             os.environ["MISOB200_CLUSTER"] = mode.split("+c")[1]
         plan.upload(params)
         plan.run_resident()
-        ms = [plan.run_resident()[0] for _ in range(3)]
+        ms = [plan.run_resident()[0] for _ in range(6)]
         bt = plan.bucket_timing()
         plan.run(params, out)
         t0 = time.perf_counter()
