@@ -109,6 +109,7 @@ struct DevState {
   cudaStream_t cstream = nullptr;          // device->host copies of finished buckets
   cudaEvent_t cdone = nullptr;
   bool uploaded = false, have_run = false;
+  bool summary_valid = false;        // d_summary holds the records of the last run
   // pinned staging of the plan's tile arena and descriptors (grow-only, pooled with the state): the
   // plan's own arrays are pageable std::vectors, and page-locking them per plan (cudaHostRegister)
   // cost 0.4 s per fresh plan while other threads of the process were allocating
@@ -1016,8 +1017,11 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
   if (kernel_ms) *kernel_ms = ms;
   if (launches) *launches = nl;
   st->have_run = true;
+  st->summary_valid = false;
   return 0;
 }
+
+int summarize_device(Plan &plan, const double **d_summary, cudaStream_t *stream);
 
 int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, int32_t *rundata,
              int32_t *status) {
@@ -1038,6 +1042,11 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
   CK(cudaEventRecord(st->ev[5], st->stream));
   CK(cudaStreamSynchronize(st->stream));
 
+  // the summary records (mean, 95% CI, assigned counts) while the host scatters the assignments: the
+  // kernel needs only what is already on the device
+  if (!std::getenv("MISOB200_NO_EAGER_SUMMARY")) {
+    if (summarize_device(plan, nullptr, nullptr) != 0) cudaGetLastError();      // (not fatal here: misob200_summarize reports it)
+  }
   // host epilogue: scatter chain-0 assignments back to input read order
   // (miso.c:943-946) and fill rundata (include/splicing.h:143-146)
   auto epilogue = [&](size_t g0, size_t g1) {
@@ -1173,7 +1182,7 @@ int summarize_device(Plan &plan, const double **d_summary, cudaStream_t *stream)
   if (d_summary) *d_summary = st->d_summary;
   if (stream) *stream = st->stream;
   const int G = (int) plan.desc.size();
-  if (G == 0) return 0;
+  if (G == 0 || st->summary_valid) return 0;      // (download() already launched it behind the chains, see there)
   const int n = (int) cols_of(st->params);      // every column of the block, like the reference's Python (samples_utils.py)
   int n_pad = 1;
   while (n_pad < n) n_pad <<= 1;
@@ -1185,6 +1194,7 @@ int summarize_device(Plan &plan, const double **d_summary, cudaStream_t *stream)
   summary_kernel<<<G, 128, smem, st->stream>>>(st->d_desc, G, st->params.n_chains, n, lo, hi, n_pad, st->d_samples,
                                               st->d_drawn, st->d_accrej, st->d_summary);
   CK(cudaGetLastError());
+  st->summary_valid = true;
   return 0;
 }
 
