@@ -64,7 +64,10 @@ constexpr unsigned kRingEmpty = 0xffffffffu;
 #endif
 
 // Pop: returns the unit of pop number p (lane 0 polls; relaxed loads served by L2 so that the
-// SM's L1 is not invalidated on every poll, one acquire fence at the end).
+// SM's L1 is not invalidated on every poll, one acquire fence at the end).  The caller broadcasts the
+// unit, __syncwarp()s, and every lane reads the hand-over record (ChainState, progress) with
+// ld.global.cg (__ldcg): L2 is the point of coherence, so a line of the same chain left in this SM's
+// L1 by an earlier segment can never be what a lane sees.
 #ifdef MISOB200_SEG_DEBUG
 __device__ unsigned long long g_seg_dbg[8];    // polls, wait cycles, pops, ring pops
 #endif
@@ -282,8 +285,8 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
   // ---- start state, splicing_drift_proposal_init (miso.c:330-447) ----------
   double alpha;            // replicated in every group: member i < K-1 holds alpha_i
   if (!fresh) {
-    alpha = st->alpha[mi < len ? mi : 0];
-    n_u = st->n_u;
+    alpha = __ldcg(&st->alpha[mi < len ? mi : 0]);      // hand-over record: read from L2 (see ring_pop)
+    n_u = __ldcg(&st->n_u);
   } else if (P.start == MISOB200_START_AUTO) {
     if (K == 2) { n_u = 1; alpha = 0.0; }     // one uniform drawn and discarded (miso.c:365)
     else alpha = 1.0 / (K - 1);
@@ -319,10 +322,10 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
   bool have_rp = false;
   if (!fresh) {            // resume: the current point is a function of alpha
     cur = derive<K>(alpha, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
-    cnt_k = st->cnt[kk];
-    rp_drawn = st->rp_drawn;
-    lagc = st->lagc; n_rec = st->n_rec; acc = st->acc; rej = st->rej;
-    have_rp = st->have_rp != 0;
+    cnt_k = __ldcg(&st->cnt[kk]);
+    rp_drawn = __ldcg(&st->rp_drawn);
+    lagc = __ldcg(&st->lagc); n_rec = __ldcg(&st->n_rec); acc = __ldcg(&st->acc); rej = __ldcg(&st->rej);
+    have_rp = __ldcg(&st->have_rp) != 0;
   }
   const int S_total = (P.n_iters - P.burn_in) / P.lag;
   uint8_t *ass_out = (chain == 0) ? P.drawn + d.drawn_off : nullptr;
@@ -533,12 +536,13 @@ __global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? 1 : (K <= 6 ? 4 : 3)))
       item = p < n_pops ? ring_pop(P.ring, p, n_items) : kRingEmpty;
     }
     item = __shfl_sync(0xffffffffu, item, 0);
+    __syncwarp();      // lane 0's acquire fence (ring_pop) ordered before the other lanes' reads of the hand-over record
     if (item == kRingEmpty) break;
     const int gi = P.items[item / (unsigned) P.n_chains];
     const int chain = (int) (item % (unsigned) P.n_chains);
     const GeneDesc &d = P.desc[gi];
     int *const progress = P.progress + ((long long) gi * P.n_chains + chain);
-    const int seg = *progress;
+    const int seg = __ldcg(progress);
     const uint32_t tile_bytes = (uint32_t) d.tile_bytes;
     ClassRef cr;
     cr.ncls = FMT == 1 ? d.ncls : 0;

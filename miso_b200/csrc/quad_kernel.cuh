@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
       unit = p < n_pops ? ring_pop(P.ring, p, n_units) : kRingEmpty;
     }
     unit = __shfl_sync(kFull, unit, 0);
+    __syncwarp();      // lane 0's acquire fence (ring_pop) before the other lanes' reads of the hand-over records
     if (unit == kRingEmpty) break;
 #ifdef MISOB200_SEG_DEBUG
     const long long dbg_t0 = clock64();
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
     const GeneDesc &d = P.desc[gi];
     ChainState *const st = P.state + ((long long) gi * P.n_chains + chain);
     int *const progress = P.progress + ((long long) gi * P.n_chains + chain);
-    const int seg = *progress;                 // the same for the four chains of a unit
+    const int seg = __ldcg(progress);                 // the same for the four chains of a unit
     const int m_begin = seg * P.seg_len - 1;
     const int m_end = min(m_begin + P.seg_len, P.n_iters);
     const bool fresh = seg == 0;
@@ -404,8 +405,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
     unsigned long long n_u = 0;
     double alpha;
     if (!fresh) {
-      alpha = st->alpha[mi < len ? mi : 0];
-      n_u = st->n_u;
+      alpha = __ldcg(&st->alpha[mi < len ? mi : 0]);      // hand-over record: read from L2 (see ring_pop)
+      n_u = __ldcg(&st->n_u);
     } else if (P.start == MISOB200_START_AUTO) {
       if (K == 2) { n_u = 1; alpha = 0.0; }     // one uniform drawn and discarded (miso.c:365)
       else alpha = 1.0 / (K - 1);
@@ -431,10 +432,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
     bool have_rp = false;
     if (!fresh) {            // resume: the current point is a function of alpha (ChainState)
       cur = derive<K>(alpha, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
-      cnt_k = st->cnt[kk];
-      rp_drawn = st->rp_drawn;
-      lagc = st->lagc; n_rec = st->n_rec; acc = st->acc; rej = st->rej;
-      have_rp = st->have_rp != 0;
+      cnt_k = __ldcg(&st->cnt[kk]);
+      rp_drawn = __ldcg(&st->rp_drawn);
+      lagc = __ldcg(&st->lagc); n_rec = __ldcg(&st->n_rec); acc = __ldcg(&st->acc); rej = __ldcg(&st->rej);
+      have_rp = __ldcg(&st->have_rp) != 0;
     }
 
     // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed by the

@@ -1,16 +1,26 @@
-"""Small run of every device layout for compute-sanitizer (memcheck / racecheck) on the GPU box:
-  compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+"""Tiny end-to-end run for compute-sanitizer (memcheck / racecheck): device setup (match_kernel,
+order_kernel), chain + quad kernels with chains cut into short segments and handed over through the
+ready queues, helper grids, zero-copy outputs, summary and comparison kernels."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("MISOB200_SEG_ITERS", "16")
+os.environ.setdefault("MISOB200_SEG_ALWAYS", "1")
+import numpy as np
 import miso_b200 as mb
-for cpw in ("4", "1"):
-    os.environ["MISOB200_CHAINS_PER_WARP"] = cpw
-    for kind, fmt, wide in ((0, -1, False), (1, -1, False), (1, 0, False), (1, -1, True)):
-        sd2 = 2500.0 if wide else 900.0
-        w = mb.Workload(kind, 23, 300, 36, 300.0 if wide else 250.0, sd2, 4.0, seed=3)
-        plan = mb.Plan(tile_format=fmt).append(w)
-        for start in (0, 2):
-            out = plan.run(mb.make_params(60, 10, 5, 2, start=start, seed=5))
-        plan.summarize()
-        plan.close()
-        print("ok cpw", cpw, "kind", kind, "fmt", fmt, "wide", wide, flush=True)
+from workloads import Workload
+
+params = mb.make_params(80, 16, 4, 2, seed=3)
+plans = []
+for smp in (0, 1):
+    w = Workload(1, 96, 160, 36, 250., 900., 4., seed=7, sample=smp)
+    p = mb.Plan().append(w, match_device=0)
+    out = p.alloc_outputs(params, pinned=True)
+    p.run(params, out)
+    assert (out["status"] == 0).all() and np.isfinite(out["samples"]).all()
+    plans.append(p)
+s = plans[0].summarize()
+c = plans[0].compare(plans[1])
+w = Workload(0, 64, 120, 36, seed=9)
+p = mb.Plan().append(w, match_device=0)
+o = p.run(mb.make_params(60, 10, 5, 1, seed=1))
+print("ok", s.shape, c.shape, o["launches"])
