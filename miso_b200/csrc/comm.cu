@@ -115,9 +115,16 @@ int allgather_device(const double *d_src, long long n, long long n_pad, int rec_
     send = g_in;
   }
   NK(N.AllGather(send, g_out, per, ncclFloat64, g_comm, g_stream));
-  CK(cudaMemcpyAsync(g_host, g_out, per * g_ranks * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  // straight into the caller's buffer when it is page-locked, else through the pinned mirror
+  bool direct = false;
+  if (all) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, all) == cudaSuccess && pa.type == cudaMemoryTypeHost) direct = true;
+    else cudaGetLastError();
+  }
+  CK(cudaMemcpyAsync(direct ? all : g_host, g_out, per * g_ranks * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CK(cudaStreamSynchronize(g_stream));
-  if (all) std::memcpy(all, g_host, per * g_ranks * sizeof(double));
+  if (all && !direct) std::memcpy(all, g_host, per * g_ranks * sizeof(double));
   return 0;
 }
 }  // namespace

@@ -443,7 +443,9 @@ int upload(Plan &plan, const misob200_params_t &p) {
       if (plan.desc[g].paired && plan.desc[g].format == 1)
         for (int k = 0; k < plan.desc[g].K; k++) max_l = std::max(max_l, plan.desc[g].L[k]);
     st->n_neglog = std::min(max_l + 1, 1 << 21);
-    st->h_neglog.assign(std::max(st->n_neglog, 2), 0.0);
+    // two spare entries: the padding reads of a tile (null class, code 0) look up lp = L_k + 1 in the unchecked
+    // read-score pass (class_pass.cuh MODE 2) before the result is discarded -- found by compute-sanitizer
+    st->h_neglog.assign((size_t) st->n_neglog + 2, 0.0);
     for (int n = 1; n < st->n_neglog; n++) st->h_neglog[n] = -std::log((double) n);
   }
 
