@@ -124,7 +124,7 @@ const char *misob200_last_error(void);
 
 /* device bring-up; fails loudly (MISOB200_ECUDA) if no sm_100 device */
 int misob200_init(int device);
-int misob200_shutdown(void);
+int misob200_shutdown(void);	/* frees the pooled device states and setup stages */
 int misob200_device_count(int *count);
 
 int misob200_plan_create(misob200_plan_t **plan);

@@ -14,7 +14,8 @@ void plan_layout(Plan &plan, const misob200_params_t &p, long long *n_samples, l
                  long long (*range)[4] = nullptr);
 int device_init(int device);
 int upload(Plan &plan, const misob200_params_t &p);
-int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples = nullptr, double *h_loglik = nullptr);
+int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples = nullptr, double *h_loglik = nullptr,
+                 int32_t *h_assignment = nullptr);
 int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, int32_t *rundata,
              int32_t *status);
 int release_device(Plan &plan);
@@ -38,7 +39,7 @@ int misob200_version(void) { return 100; }
 const char *misob200_last_error(void) { return last_error(); }
 
 int misob200_init(int device) { return device_init(device); }
-int misob200_shutdown(void) { return release_pool(); }
+int misob200_shutdown(void) { stage_pool_release(); return release_pool(); }
 int misob200_device_count(int *count) { return device_count(count); }
 
 int misob200_plan_create(misob200_plan_t **plan) {
@@ -250,7 +251,7 @@ int misob200_run(misob200_plan_t *plan, const misob200_params_t *params, double 
   auto t1 = now();
   // pinned output buffers are written by the kernels themselves; download() then only fetches
   // the assignments and counters
-  if (int rc = run_resident(plan->p, nullptr, launches, samples, loglik)) return rc;
+  if (int rc = run_resident(plan->p, nullptr, launches, samples, loglik, assignment)) return rc;
   auto t2 = now();
   if (int rc = download(plan->p, nullptr, nullptr, assignment, rundata, status)) return rc;
   run_timing(plan->p, timing_ms);

@@ -214,6 +214,22 @@ void last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, long lo
   if (bytes_out) *bytes_out = t_bytes_out;
 }
 
+// frees the buffers of every idle stage (misob200_shutdown)
+void stage_pool_release() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (Stage &p : g_stage) {
+    if (p.busy || p.device < 0) continue;
+    cudaSetDevice(p.device);
+    for (auto &x : p.d) { cudaFree(x); x = nullptr; }
+    for (auto &c : p.cap) c = 0;
+    for (auto &x : p.h) { if (x) cudaFreeHost(x); x = nullptr; }
+    for (auto &c : p.hcap) c = 0;
+    if (p.stream) { cudaStreamDestroy(p.stream); p.stream = nullptr; }
+    for (auto &e : p.ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+    p.device = -1;
+  }
+}
+
 void stage_release(int stage) {
   if (stage < 0 || stage >= kStages) return;
   {

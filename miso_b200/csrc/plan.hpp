@@ -110,6 +110,7 @@ int stage_submit(const misob200_reads_t &reads, const MatchParams &mp, int devic
                  const std::vector<uint16_t> &code_rank, DeviceCodes &out);
 int stage_wait(DeviceCodes &out);
 void stage_release(int stage);
+void stage_pool_release();
 // timing of the last device matching of this thread's plan_append (ms; bytes)
 void last_match_stats(double *kernel_ms, double *h2d_ms, double *d2h_ms, long long *bytes_in, long long *bytes_out);
 

@@ -110,6 +110,7 @@ struct DevState {
   cudaEvent_t cdone = nullptr;
   bool uploaded = false, have_run = false;
   bool summary_valid = false;        // d_summary holds the records of the last run
+  const int32_t *prefilled = nullptr;      // assignment buffer run_resident pre-filled during the last run
   // pinned staging of the plan's tile arena and descriptors (grow-only, pooled with the state): the
   // plan's own arrays are pageable std::vectors, and page-locking them per plan (cudaHostRegister)
   // cost 0.4 s per fresh plan while other threads of the process were allocating
@@ -748,7 +749,28 @@ static int fire(Launch &L, long long blocks, cudaStream_t stream, int cluster = 
   return 0;
 }
 
-int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples, double *h_loglik) {
+// The part of the output epilogue that does not depend on the run -- every read's assignment
+// starts as -1 / its only compatible isoform (miso.c:943-946 for the reads that never draw) -- is
+// written while the chain kernels run and the host has nothing else to do; download() then only
+// scatters the drawn reads.
+static void prefill_assignment(const Plan &plan, int32_t *assignment) {
+  const size_t G = plan.host.size();
+  auto fill = [&](size_t g0, size_t g1) {
+    for (size_t g = g0; g < g1; g++) {
+      const GeneHost &h = plan.host[g];
+      int32_t *a = assignment + h.read_base;
+      if (h.status == 0) for (int r = 0; r < h.R; r++) a[r] = h.fixed_ass[r];
+      else for (int r = 0; r < h.R; r++) a[r] = -1;
+    }
+  };
+  unsigned nt = G < 256 ? 1u : (unsigned) host_threads();
+  if (nt == 1) { fill(0, G); return; }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nt; t++) pool.emplace_back(fill, G * t / nt, G * (t + 1) / nt);
+  for (auto &t : pool) t.join();
+}
+
+int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples, double *h_loglik, int32_t *h_assignment) {
   DevState *st = static_cast<DevState *>(plan.dev);
   if (!st || !st->uploaded) { set_error("run_resident: plan is not on the device (call misob200_upload)"); return MISOB200_EINVAL; }
   CK(cudaSetDevice(st->device));
@@ -961,6 +983,8 @@ int run_resident(Plan &plan, double *kernel_ms, int *launches, double *h_samples
     CK(cudaStreamWaitEvent(st->stream, st->kdone[b], 0));
   }
   CK(cudaEventRecord(st->ev[3], st->stream));
+  st->prefilled = nullptr;
+  if (h_assignment) { prefill_assignment(plan, h_assignment); st->prefilled = h_assignment; }
   if (h_samples || h_loglik) {
     // genes that did not run (status != 0): their zeroed blocks, the tail of the layout; and
     // buckets skipped by a development switch
@@ -1051,6 +1075,8 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
   }
   // host epilogue: scatter chain-0 assignments back to input read order
   // (miso.c:943-946) and fill rundata (include/splicing.h:143-146)
+  const bool prefilled = assignment && st->prefilled == assignment;      // (run_resident wrote the run-independent part)
+  st->prefilled = nullptr;
   auto epilogue = [&](size_t g0, size_t g1) {
     for (size_t g = g0; g < g1; g++) {
       const GeneHost &h = plan.host[g];
@@ -1070,7 +1096,7 @@ int download(Plan &plan, double *samples, double *loglik, int32_t *assignment, i
       }
       if (assignment) {
         int32_t *a = assignment + h.read_base;
-        for (int r = 0; r < h.R; r++) a[r] = h.status == 0 ? h.fixed_ass[r] : -1;
+        if (!prefilled) for (int r = 0; r < h.R; r++) a[r] = h.status == 0 ? h.fixed_ass[r] : -1;
         if (h.status == 0) {
           const uint8_t *dr = st->h_drawn + d.drawn_off;
           for (int i = 0; i < h.R2; i++) a[h.rank_read[i]] = dr[i];
