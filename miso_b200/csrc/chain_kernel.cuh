@@ -168,90 +168,136 @@ struct Derived {
   double lp;       // member k < K    : normalised log psi (score_iso, miso.c:136-149)
   double q;        // member i < K-1  : log(psi_i / psi_rest) (mvplogisnorm, miso.c:113)
   double dir;      // group-uniform   : ldirichlet (miso.c:165-182)
-  double prod;     // group-uniform   : 1 / prod(theta) / ltheta (miso.c:110)
+  double slg;      // group-uniform   : sum_k log psi_k = -log(1 / prod(theta) / ltheta) (miso.c:104-110), see derive
 };
 
-#ifndef MISOB200_ROLL_FROM_K
-#define MISOB200_ROLL_FROM_K 7      /* K-wide shuffle sums are rolled loops from this K on (see derive) */
+// ---- N-wide reductions inside a lane group ---------------------------------------------
+// Two shapes, both leave the same bits in all EIGHT lanes of the group (idle members included: what
+// is decided from these values -- accept, stream position, pass type -- has to stay group-uniform):
+//   gather : every lane fetches the N members' terms (2 N shuffles, all independent) and adds them
+//            pairwise: latency of ONE shuffle + log2(N) additions, 3 N instructions;
+//   fold   : xor butterfly over the eight lanes (members >= N pass the identity): 9 instructions
+//            whatever N is, but three DEPENDENT shuffle + add rounds.
+// The chain is latency-bound (16 warps per SM), so the short dependency chain wins while N is small
+// and the instruction count wins at N = 7, 8 (profiles/r3_ab2_reductions.log); kGatherMax is the
+// largest N that gathers.  The reference adds the terms one after the other; the sums here differ
+// from its by fp64 rounding only -- like the exp / log they are built from, which CUDA and glibc already
+// round differently (parity contract).
+#ifndef MISOB200_GATHER_MAX
+#define MISOB200_GATHER_MAX 4
 #endif
-constexpr int kRollFromK = MISOB200_ROLL_FROM_K;
+constexpr int kGatherMax = MISOB200_GATHER_MAX;
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+struct OpAdd { static __device__ __forceinline__ double id() { return 0.0; }
+               static __device__ __forceinline__ double f(double a, double b) { return a + b; } };
+struct OpMax { static __device__ __forceinline__ double id() { return -INFINITY; }       // NaN members are ignored
+               static __device__ __forceinline__ double f(double a, double b) { return fmax(a, b); } };
+template <int N, class OP> __device__ __forceinline__ double group_reduce(double v, int gb, int mi) {
+  if (N <= kGatherMax) {
+    double a[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) a[i] = shfl_d(v, gb + i);
+#pragma unroll
+    for (int w = 1; w < N; w <<= 1)
+#pragma unroll
+      for (int i = 0; i + w < N; i += 2 * w) a[i] = OP::f(a[i], a[i + w]);
+    return a[0];
+  }
+  v = mi < N ? v : OP::id();
+  v = OP::f(v, shfl_xor_d(v, 1));
+  v = OP::f(v, shfl_xor_d(v, 2));
+  v = OP::f(v, shfl_xor_d(v, 4));
+  return v;
+}
+template <int N> __device__ __forceinline__ double group_add(double v, int gb, int mi) { return group_reduce<N, OpAdd>(v, gb, mi); }
+template <int N> __device__ __forceinline__ double group_max(double v, int gb, int mi) { return group_reduce<N, OpMax>(v, gb, mi); }
+
+// mvplogisnorm (miso.c:97-122) evaluates log(covar * (1 / prod(theta) / ltheta) * exp(expPart)) with
+// theta = psi_0..K-2, ltheta = 1 - sum(theta) = psi_{K-1} and tmp_i = log(theta_i / ltheta) - mu_i.
+// In log space that is  log(covar) - sum_k log psi_k + expPart  and  tmp_i = log psi_i - log psi_{K-1} - mu_i:
+// the K logs are already there (score_iso needs them), so the proposal densities cost no exp, no log and
+// no division of their own.  The two forms agree to fp64 rounding as long as nothing under- or overflows
+// on the literal route; kTameSlg / kTameExp fence that region off (every log psi_k in (-600, 0], so
+// prod(theta) >= e^-600; expPart > -700, so exp() stays normal) and anything outside -- a psi of 0, NaN,
+// a proposal hundreds of sigmas away -- is evaluated literally, operation by operation, by the *_literal
+// bodies below (cold: a chain does not live there, the prior and the likelihood are -inf or NaN too).
+constexpr double kTameSlg = -600.0, kTameExp = -700.0;
+
 // gb = first lane of this lane's group, mi = member index (lane - gb)
 template <int K>
 __device__ __forceinline__ Derived derive(double alpha, double offset_k, double hyper_m1_k,
                                           double lg_sum, double lg_each, int gb, int mi) {
   constexpr int len = K - 1;
-  // The K-wide serial sums below are unrolled for K <= 6 only: at K = 8 the unrolled 64-bit
-  // shuffles of this function alone were ~3 KB of code, and the per-iteration instruction
-  // footprint of the K = 7, 8 kernels sat right at the 32 KB instruction cache (ncu: "no
-  // instruction" was the largest stall, 2-3 cycles per issue).  Rolled loops keep the
-  // reference's summation order and cost a few more dynamic instructions: K = 8 192 -> 179 ms,
-  // K = 7 159 -> 154 ms, but K = 6 130 -> 136 ms (profiles/r1_ab14_rolled_shuffles.log).
-  constexpr int U = K < kRollFromK ? K : 1;
   Derived r;
+  // (idle members, mi >= K, carry copies of member 0 / K-1 operands: finite values that keep exp, log and
+  // the division on their fast paths; they are masked out of every reduction)
   const double e = d_exp(alpha);
-  double sumexp = 0.0;
-#pragma unroll (U)
-  for (int i = 0; i < len; i++) sumexp = sumexp + shfl_d(e, gb + i);
-  sumexp = sumexp + 1.0;
+  const double sumexp = group_add<len>(e, gb, mi) + 1.0;
   double psi = d_div(e, sumexp);
-  double sumpsi = 0.0;
-#pragma unroll (U)
-  for (int i = 0; i < len; i++) sumpsi = sumpsi + shfl_d(psi, gb + i);
+  const double sumpsi = group_add<len>(psi, gb, mi);
   if (mi == len) psi = 1 - sumpsi;
   r.psi = psi;
 
   const double lg = d_log(psi);
   const double t = lg + offset_k;
-  double mx = shfl_d(t, gb);
-#pragma unroll (U)
-  for (int i = 1; i < K; i++) {
-    const double v = shfl_d(t, gb + i);
-    if (v > mx) mx = v;
-  }
+  const double mx = group_max<K>(t, gb, mi);
   const double ex = d_exp(t - mx);
-  double sum = 0.0;
-#pragma unroll (U)
-  for (int i = 0; i < K; i++) sum = sum + shfl_d(ex, gb + i);
-  sum = d_log(sum) + mx;
+  const double sum = d_log(group_add<K>(ex, gb, mi)) + mx;
   r.lp = t - sum;
 
-  const double term = hyper_m1_k * lg;
-  double dir = 0.0;
-#pragma unroll (U)
-  for (int i = 0; i < K; i++) dir = dir + shfl_d(term, gb + i);
-  dir = dir + lg_sum;
-  dir = dir - lg_each;
-  r.dir = dir;
-
-  double lth = 1.0, prod = 1.0;
-#pragma unroll (U)
-  for (int i = 0; i < len; i++) {
-    const double at = shfl_d(psi, gb + i);
-    lth = lth - at;
-    prod = prod * at;
-  }
-  r.prod = d_div(d_div(1.0, prod), lth);
-  r.q = d_log(d_div(psi, lth));
+  r.dir = (group_add<K>(hyper_m1_k * lg, gb, mi) + lg_sum) - lg_each;
+  r.slg = group_add<K>(lg, gb, mi);
+  r.q = lg - shfl_d(lg, gb + len);
   return r;
 }
 
-// sum_k n_k * v_k in isoform order within the lane's group, skipping isoforms nothing
-// is assigned to
+// The literal route of mvplogisnorm for one (theta, mu) pair of a group: member i < K-1 holds theta_i
+// and mu_i; returns the score (group-uniform).  Operation order as miso.c:104-119.
 template <int K>
-__device__ __forceinline__ double count_dot_body(int cnt_k, double v_k, int gb) {
-  const double a = cnt_k ? (double) cnt_k * v_k : 0.0;
-  double s = 0.0;
-#pragma unroll (K < kRollFromK ? K : 1)
-  for (int i = 0; i < K; i++) s = s + shfl_d(a, gb + i);
-  return s;
+__device__ __noinline__ double proposal_score_literal(double theta, double mu, double sigma, double covar, int gb) {
+  constexpr int len = K - 1;
+  double lth = 1.0, prod = 1.0;
+#pragma unroll 1
+  for (int i = 0; i < len; i++) {
+    const double at = shfl_d(theta, gb + i);
+    lth = lth - at;
+    prod = prod * at;
+  }
+  prod = d_div(d_div(1.0, prod), lth);
+  const double tmp = d_log(d_div(theta, lth)) - mu;
+  const double e = d_div((-0.5) * tmp * tmp, sigma);
+  double ep = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < len; i++) ep = ep + shfl_d(e, gb + i);
+  return d_log(covar * prod * d_exp(ep));
 }
+
+// ptoCS (theta = psi, mu = alphaNew) and ctoPS (theta = psiNew, mu = alpha) of miso.c:531-534 for
+// every group at once.  lcovar = log(covar).
 template <int K>
-__device__ __noinline__ double count_dot_shared(int cnt_k, double v_k, int gb) { return count_dot_body<K>(cnt_k, v_k, gb); }
-// (K >= 7: one shared body for the three calls of an iteration, see derive)
+__device__ __forceinline__ void proposal_scores(const Derived &cur, double alpha, const Derived &nw, double alphaN,
+                                                double sigma, double covar, double lcovar, int gb, int mi,
+                                                double &ptoCS, double &ctoPS) {
+  constexpr int len = K - 1;
+  const double t1 = cur.q - alphaN;
+  const double t2 = nw.q - alpha;
+  const double e1 = d_div((-0.5) * t1 * t1, sigma), e2 = d_div((-0.5) * t2 * t2, sigma);
+  const double ep1 = group_add<len>(e1, gb, mi), ep2 = group_add<len>(e2, gb, mi);
+  ptoCS = (lcovar - cur.slg) + ep1;
+  ctoPS = (lcovar - nw.slg) + ep2;
+  const bool tame = cur.slg > kTameSlg && nw.slg > kTameSlg && ep1 > kTameExp && ep2 > kTameExp;
+  if (__any_sync(0xffffffffu, !tame)) {
+    const double lit1 = proposal_score_literal<K>(cur.psi, alphaN, sigma, covar, gb);
+    const double lit2 = proposal_score_literal<K>(nw.psi, alpha, sigma, covar, gb);
+    if (!tame) { ptoCS = lit1; ctoPS = lit2; }
+  }
+}
+
+// sum_k n_k * v_k over the lane's group, skipping isoforms nothing is assigned to
+// (the reference adds one term per read, miso.c:267-271 / :136-149: same value up to rounding)
 template <int K>
-__device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb) {
-  if (K >= kRollFromK) return count_dot_shared<K>(cnt_k, v_k, gb);
-  return count_dot_body<K>(cnt_k, v_k, gb);
+__device__ __forceinline__ double count_dot(int cnt_k, double v_k, int gb, int mi) {
+  return group_add<K>(cnt_k ? (double) cnt_k * v_k : 0.0, gb, mi);
 }
 
 template <int K, bool SMEM, bool WIDE, int FMT, int ROUNDS>
@@ -268,13 +314,14 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
   const int nfix_k = d.n_fixed[kk];
   const double lg_sum = d.lg_sum, lg_each = d.lg_each;
   const double sigma = d.sigma, sd = d.sd, covar = d.covar_const;
+  const double lcovar = d_log(covar);
   const int R2 = d.R2, row_bytes = d.row_bytes, flag_off = d.flag_off, paired = d.paired;
   const int ucode_off = d.ucode_off;
   const bool lp_safe = d.lp_safe != 0 && d.lp_max < P.n_neglog;
   int g_always[K];
 #pragma unroll
   for (int k = 0; k < K; k++) g_always[k] = FMT == 1 ? d.g_always[k] : 0;
-  int thr_state = 0;       // class format: 0 thresholds stale (psi changed), 1 valid, 2 declined for this psi
+  int thr_state = 0;       // class format: 0 thresholds stale (psi changed), 1 valid, 2 declined for this psi / fast rule not applicable
   const uint32_t gid = d.gene_id;
   const PhiloxKeyT<ROUNDS> &key = P.key;
   const int *L = d.L;
@@ -313,7 +360,7 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
   double zbuf1 = stream_normal(zbase + 32u + (uint32_t) lane, gid, (uint32_t) chain, key);
 
   Derived cur;             // replicated in every group
-  cur.psi = cur.lp = cur.q = cur.dir = cur.prod = 0.0;
+  cur.psi = cur.lp = cur.q = cur.dir = cur.slg = 0.0;
   double psi_r[K];
   int cnt[K];
   int cnt_k = 0;           // member k: reads currently assigned to isoform k (every group)
@@ -333,8 +380,11 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
   auto do_pass = [&](int m_next) {
     const bool last = (m_next >= P.n_iters);
     const bool rec_next = d.rp_always || (paired && m_next >= P.burn_in && lagc == P.lag - 1);
+    // The fast rules hold for every read of a pass iff no psi is NaN and the smallest weight stays
+    // normal; that and the thresholds depend on psi only: re-examined after an accept (thr_state 0),
+    // not on every pass (class format; dense tiles pass psi itself to the pass).
     bool ok = false;
-    if (!(last && ass_out)) {
+    if (!(last && ass_out) && (FMT == 0 || thr_state == 0)) {
       double pmin = 1.0;
 #pragma unroll
       for (int k = 0; k < K; k++) {
@@ -343,7 +393,9 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
         ok = ok || !(psi_r[k] == psi_r[k]);             // ... so flag it here
       }
       ok = !ok && (pmin * P.ptab_min >= 1e-290);        // fast rule valid for every read of this pass
+      if (FMT == 1) thr_state = (ok && !thr_update<K>(cr, ptab_s, psi_r)) ? 1 : 2;
     }
+    if (FMT == 1) ok = !(last && ass_out) && thr_state == 1;
     int c = 0;             // member k: drawing reads assigned to isoform k
     if (FMT == 0) {
       if (ok) {
@@ -360,8 +412,6 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
                                   L, &c, &rp_drawn, last ? ass_out : nullptr);
       }
     } else {
-      if (ok && thr_state == 0) thr_state = thr_update<K>(cr, ptab_s, psi_r) ? 2 : 1;
-      ok = ok && thr_state == 1;
       if (ok && !(rec_next && !last && paired)) {
         class_pass<K, SMEM>(rows, cr, n_u, R2, gid, (uint32_t) chain, key, g_always, cnt);
 #pragma unroll
@@ -386,7 +436,7 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
   bool batch_ok = false;
   double alphaB = 0.0, scP = 0.0, scC = 0.0;
   Derived nwB;
-  nwB.psi = nwB.lp = nwB.q = nwB.dir = nwB.prod = 0.0;
+  nwB.psi = nwB.lp = nwB.q = nwB.dir = nwB.slg = 0.0;
 
   auto make_batch = [&](int m) {
     m0 = m;
@@ -403,19 +453,8 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
     const double z = zi < 32u ? za : zb;
     alphaB = alpha + sd * z;
     nwB = derive<K>(alphaB, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
-    // ---- proposal densities (miso.c:531-534, :97-122): member 0 evaluates the density of
-    // the current point seen from the proposal, member 1 the reverse
-    const double t1 = cur.q - alphaB;                        // theta = psi,    mu = alphaNew
-    const double t2 = nwB.q - alpha;                         // theta = psiNew, mu = alpha
-    const double e1 = d_div((-0.5) * t1 * t1, sigma), e2 = d_div((-0.5) * t2 * t2, sigma);
-    double ep1 = 0.0, ep2 = 0.0;
-#pragma unroll (K < kRollFromK ? K - 1 : 1)
-    for (int i = 0; i < len; i++) { ep1 = ep1 + shfl_d(e1, gb + i); ep2 = ep2 + shfl_d(e2, gb + i); }
-    const double xe = d_exp(mi == 0 ? ep1 : ep2);
-    const double pdf = covar * (mi == 0 ? cur.prod : nwB.prod) * xe;
-    const double sc = d_log(pdf);
-    scP = shfl_d(sc, gb);            // ptoCS
-    scC = shfl_d(sc, gb + 1);        // ctoPS
+    // ---- proposal densities (miso.c:531-534, :97-122), see proposal_scores
+    proposal_scores<K>(cur, alpha, nwB, alphaB, sigma, covar, lcovar, gb, mi, scP, scC);     // ptoCS, ctoPS
   };
 
   // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed
@@ -426,15 +465,15 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
     if (m < 0) {
       alpha = shfl_d(alphaB, src);
       cur.psi = shfl_d(nwB.psi, src); cur.lp = shfl_d(nwB.lp, src); cur.q = shfl_d(nwB.q, src);
-      cur.dir = shfl_d(nwB.dir, src); cur.prod = shfl_d(nwB.prod, src);
+      cur.dir = shfl_d(nwB.dir, src); cur.slg = shfl_d(nwB.slg, src);
       batch_ok = false; thr_state = 0;
     } else {
     // ---- joint scores (miso.c:524-529); every group scores its own proposal --------
     double rp;
-    if (!paired) rp = count_dot<K>(cnt_k, rs_se_k, gb);      // sum_r isoscores[ass_r], miso.c:267-271
+    if (!paired) rp = count_dot<K>(cnt_k, rs_se_k, gb, mi);      // sum_r isoscores[ass_r], miso.c:267-271
     else rp = have_rp ? d.rp_fixed + rp_drawn : 0.0;        // cancels in the ratio when not recorded
-    const double ppJS_g = rp + count_dot<K>(cnt_k, nwB.lp, gb) + nwB.dir;
-    const double pcJS = rp + count_dot<K>(cnt_k, cur.lp, gb) + cur.dir;
+    const double ppJS_g = rp + count_dot<K>(cnt_k, nwB.lp, gb, mi) + nwB.dir;
+    const double pcJS = rp + count_dot<K>(cnt_k, cur.lp, gb, mi) + cur.dir;
     const double acceptP_g = d_exp((m > 0) ? ppJS_g + scP - (pcJS + scC) : ppJS_g - pcJS);
     const double acceptP = shfl_d(acceptP_g, src & 24);
 
@@ -450,7 +489,7 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
       cJS = shfl_d(ppJS_g, src & 24);
       alpha = shfl_d(alphaB, src);
       cur.psi = shfl_d(nwB.psi, src); cur.lp = shfl_d(nwB.lp, src); cur.q = shfl_d(nwB.q, src);
-      cur.dir = shfl_d(nwB.dir, src); cur.prod = shfl_d(nwB.prod, src);
+      cur.dir = shfl_d(nwB.dir, src); cur.slg = shfl_d(nwB.slg, src);
       acc++; thr_state = 0; batch_ok = false;
     } else {
       rej++;

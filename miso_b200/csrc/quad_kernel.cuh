@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
     const int nfix_k = d.n_fixed[kk];
     const double lg_sum = d.lg_sum, lg_each = d.lg_each;
     const double sigma = d.sigma, sd = d.sd, covar = d.covar_const, rp_fixed = d.rp_fixed;
+    const double lcovar = d_log(covar);
     const int R2 = d.R2, paired = d.paired, rp_always = d.rp_always;
     const uint32_t gid = d.gene_id;
     int g_always[K];
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
     }
 
     Derived cur;
-    cur.psi = cur.lp = cur.q = cur.dir = cur.prod = 0.0;
+    cur.psi = cur.lp = cur.q = cur.dir = cur.slg = 0.0;
     int cnt_k = 0;
     double rp_drawn = 0.0;
     int lagc = 0, n_rec = 0, acc = 0, rej = 0;
@@ -438,36 +439,41 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
       have_rp = __ldcg(&st->have_rp) != 0;
     }
 
+    // normals are produced eight at a time per chain into a 16-entry window (member l of a group
+    // holds normals zbase + l and zbase + 8 + l of its chain): one Box-Muller evaluation per 8 / (K-1)
+    // iterations instead of one per iteration.  The four chains run the same iteration, so the
+    // window position is warp-uniform.
+    uint32_t zbase = ((uint32_t) (m_begin + 1) * (uint32_t) len) & ~7u;
+    double zbuf0 = stream_normal(zbase + (uint32_t) mi, gid, (uint32_t) chain, key);
+    double zbuf1 = stream_normal(zbase + 8u + (uint32_t) mi, gid, (uint32_t) chain, key);
+
     // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed by the
     // initial assignment (miso.c:840-843); m >= 0 are the iterations proper.
     for (int m = m_begin; m < m_end; m++) {
       // ---- propose (miso.c:851): alphaNew = alpha + sd * N(0,1); normals (m+1)(K-1) .. +K-2
-      const double z = stream_normal((uint32_t) (m + 1) * (uint32_t) len + (uint32_t) (mi < len ? mi : 0), gid,
-                                     (uint32_t) chain, key);
+      const uint32_t first = (uint32_t) (m + 1) * (uint32_t) len;
+      if (first - zbase >= 8u) {             // slide the window (first grows by len < 8 per iteration; warp-uniform)
+        zbase += 8u;
+        zbuf0 = zbuf1;
+        zbuf1 = stream_normal(zbase + 8u + (uint32_t) mi, gid, (uint32_t) chain, key);
+      }
+      const uint32_t zi = first - zbase + (uint32_t) (mi < len ? mi : 0);        // < 8 + len <= 14
+      const double za = shfl_d(zbuf0, gb + (int) (zi & 7u)), zb = shfl_d(zbuf1, gb + (int) (zi & 7u));
+      const double z = zi < 8u ? za : zb;
       const double alphaN = alpha + sd * z;
       const Derived nw = derive<K>(alphaN, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
       bool accept = true;
       double cJS = 0.0;
       if (m >= 0) {
-        // ---- proposal densities (miso.c:531-534, :97-122): member 0 evaluates the density of
-        // the current point seen from the proposal, member 1 the reverse
-        const double t1 = cur.q - alphaN;                        // theta = psi,    mu = alphaNew
-        const double t2 = nw.q - alpha;                          // theta = psiNew, mu = alpha
-        const double e1 = d_div((-0.5) * t1 * t1, sigma), e2 = d_div((-0.5) * t2 * t2, sigma);
-        double ep1 = 0.0, ep2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < len; i++) { ep1 = ep1 + shfl_d(e1, gb + i); ep2 = ep2 + shfl_d(e2, gb + i); }
-        const double xe = d_exp(mi == 0 ? ep1 : ep2);
-        const double pdf = covar * (mi == 0 ? cur.prod : nw.prod) * xe;
-        const double sc = d_log(pdf);
-        const double scP = shfl_d(sc, gb);             // ptoCS
-        const double scC = shfl_d(sc, gb + 1);         // ctoPS
+        // ---- proposal densities (miso.c:531-534, :97-122), see proposal_scores (chain_kernel.cuh)
+        double scP, scC;                                   // ptoCS, ctoPS
+        proposal_scores<K>(cur, alpha, nw, alphaN, sigma, covar, lcovar, gb, mi, scP, scC);
         // ---- joint scores (miso.c:524-529) ------------------------------------------------
         double rp;
-        if (!paired) rp = count_dot<K>(cnt_k, rs_se_k, gb);       // sum_r isoscores[ass_r], miso.c:267-271
+        if (!paired) rp = count_dot<K>(cnt_k, rs_se_k, gb, mi);       // sum_r isoscores[ass_r], miso.c:267-271
         else rp = have_rp ? rp_fixed + rp_drawn : 0.0;           // cancels in the ratio when not recorded
-        const double ppJS = rp + count_dot<K>(cnt_k, nw.lp, gb) + nw.dir;
-        const double pcJS = rp + count_dot<K>(cnt_k, cur.lp, gb) + cur.dir;
+        const double ppJS = rp + count_dot<K>(cnt_k, nw.lp, gb, mi) + nw.dir;
+        const double pcJS = rp + count_dot<K>(cnt_k, cur.lp, gb, mi) + cur.dir;
         const double acceptP = d_exp((m > 0) ? ppJS + scP - (pcJS + scC) : ppJS - pcJS);
         // ---- accept (miso.c:869-880): the uniform is consumed only if !(acceptP >= 1) ------
         const bool sure = acceptP >= 1;

@@ -21,8 +21,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
             os.environ["MISOB200_ONLY_K"] = str(k)
         else:
             os.environ.pop("MISOB200_ONLY_K", None)
-        best = min(plan.run_resident()[0] for _ in range(2))
+        best = min(plan.run_resident()[0] for _ in range(2 if k else 3))
         out.append("%s %.1f" % ("K%d" % k if k else "all", best))
+    if kind and not os.environ.get('AB_ALL_ONLY'):
+        out.append("buckets " + " ".join("%.0f" % x for x in plan.bucket_timing() if x > 0))
     print("kind %d G %d: " % (kind, G) + "  ".join(out) + "  -> %.4g it/s" % (G * 5000 / (best / 1e3)), flush=True)
     plan.close()
     sys.exit(0)
