@@ -63,17 +63,21 @@ constexpr unsigned kRingEmpty = 0xffffffffu;
 #define MISOB200_POLL_NS 500
 #endif
 
-// Pop: returns the unit of pop number p (lane 0 polls; relaxed loads served by L2 so that the
-// SM's L1 is not invalidated on every poll, one acquire fence at the end).  The caller broadcasts the
-// unit, __syncwarp()s, and every lane reads the hand-over record (ChainState, progress) with
-// ld.global.cg (__ldcg): L2 is the point of coherence, so a line of the same chain left in this SM's
-// L1 by an earlier segment can never be what a lane sees.
+// Pop: returns the unit of pop number p.  The WHOLE warp polls (one relaxed load of the same word per
+// trip, served by L2 so that the SM's L1 is not invalidated on every poll; one acquire fence at the end):
+// a loop that only lane 0 runs leaves the warp split into {lane 0} and {lanes 1..31} -- the compiler
+// cannot mark a region with a sleep loop reconvergent -- and a split warp issues every instruction of
+// the following segment twice and takes the divergent fall-back of every shuffle
+// (profiles/r3_k8_split_warps.txt: 22 % of the popped segments ran that way, the "slow resumed
+// segments" of round 1).  After the fence every lane reads the hand-over record (ChainState, progress)
+// with ld.global.cg (__ldcg): L2 is the point of coherence, so a line of the same chain left in this
+// SM's L1 by an earlier segment can never be what a lane sees.
 #ifdef MISOB200_SEG_DEBUG
 __device__ unsigned long long g_seg_dbg[8];    // polls, wait cycles, pops, ring pops
 #endif
 __device__ __forceinline__ unsigned ring_pop(const unsigned *ring, unsigned p, unsigned n_units) {
 #ifdef MISOB200_SEG_DEBUG
-  atomicAdd(&g_seg_dbg[2], 1ull);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&g_seg_dbg[2], 1ull);
 #endif
   if (p < n_units) return p;
   const unsigned *slot = ring + (p - n_units);
@@ -84,6 +88,7 @@ __device__ __forceinline__ unsigned ring_pop(const unsigned *ring, unsigned p, u
 #endif
   while (true) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(slot) : "memory");
+    v = __shfl_sync(0xffffffffu, v, 0);          // one value for the warp: the loop stays uniform
     if (v != kRingEmpty) break;
     __nanosleep(MISOB200_POLL_NS);
 #ifdef MISOB200_SEG_DEBUG
@@ -91,11 +96,14 @@ __device__ __forceinline__ unsigned ring_pop(const unsigned *ring, unsigned p, u
 #endif
   }
 #ifdef MISOB200_SEG_DEBUG
-  atomicAdd(&g_seg_dbg[0], polls);
-  atomicAdd(&g_seg_dbg[1], (unsigned long long) (clock64() - t0));
-  atomicAdd(&g_seg_dbg[3], 1ull);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&g_seg_dbg[0], polls);
+    atomicAdd(&g_seg_dbg[1], (unsigned long long) (clock64() - t0));
+    atomicAdd(&g_seg_dbg[3], 1ull);
+  }
 #endif
   __threadfence();
+  __syncwarp();
   return v;
 }
 // Push: the caller's ChainState stores are ordered before the slot by the fence.
@@ -569,13 +577,10 @@ __global__ void __launch_bounds__(WARPS * 32, (FMT == 1 ? 1 : (K <= 6 ? 4 : 3)))
   const unsigned n_pops = n_items * (unsigned) P.n_seg;
   uint32_t phase = 0;
   while (true) {
-    unsigned item = 0;
-    if (lane == 0) {
-      const unsigned p = atomicAdd(P.queue, 1u);
-      item = p < n_pops ? ring_pop(P.ring, p, n_items) : kRingEmpty;
-    }
-    item = __shfl_sync(0xffffffffu, item, 0);
-    __syncwarp();      // lane 0's acquire fence (ring_pop) ordered before the other lanes' reads of the hand-over record
+    unsigned p = 0;
+    if (lane == 0) p = atomicAdd(P.queue, 1u);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    const unsigned item = p < n_pops ? ring_pop(P.ring, p, n_items) : kRingEmpty;      // warp-uniform
     if (item == kRingEmpty) break;
     const int gi = P.items[item / (unsigned) P.n_chains];
     const int chain = (int) (item % (unsigned) P.n_chains);

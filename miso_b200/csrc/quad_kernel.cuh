@@ -334,13 +334,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
   const int S_total = (P.n_iters - P.burn_in) / P.lag;
   uint32_t phase = 0;
   while (true) {
-    unsigned unit = 0;
-    if (lane == 0) {
-      const unsigned p = atomicAdd(P.queue, 1u);
-      unit = p < n_pops ? ring_pop(P.ring, p, n_units) : kRingEmpty;
-    }
-    unit = __shfl_sync(kFull, unit, 0);
-    __syncwarp();      // lane 0's acquire fence (ring_pop) before the other lanes' reads of the hand-over records
+    unsigned p = 0;
+    if (lane == 0) p = atomicAdd(P.queue, 1u);
+    p = __shfl_sync(kFull, p, 0);
+    const unsigned unit = p < n_pops ? ring_pop(P.ring, p, n_units) : kRingEmpty;      // the whole warp polls (ring_pop)
     if (unit == kRingEmpty) break;
 #ifdef MISOB200_SEG_DEBUG
     const long long dbg_t0 = clock64();
