@@ -122,6 +122,7 @@ template <int ROUNDS> struct ChainParamsT {
   const double *ptab;
   int n_ptab;
   double ptab_min;           // smallest non-zero entry of ptab
+  double tame_slg;           // proposal densities in log space while sum_k log psi_k > tame_slg (kTameSlg; see proposal_scores)
   double *samples;
   double *loglik;
   // optional second destination of every recorded sample: the caller's PINNED host buffers, written
@@ -229,6 +230,8 @@ template <int N> __device__ __forceinline__ double group_max(double v, int gb, i
 // prod(theta) >= e^-600; expPart > -700, so exp() stays normal) and anything outside -- a psi of 0, NaN,
 // a proposal hundreds of sigmas away -- is evaluated literally, operation by operation, by the *_literal
 // bodies below (cold: a chain does not live there, the prior and the likelihood are -inf or NaN too).
+// The bound on sum_k log psi_k travels in ChainParams.tame_slg: MISOB200_LITERAL_SCORES=1 sets it to +1
+// (never tame), which sends every proposal down the literal route -- how the tests reach that code.
 constexpr double kTameSlg = -600.0, kTameExp = -700.0;
 
 // gb = first lane of this lane's group, mi = member index (lane - gb)
@@ -284,8 +287,8 @@ __device__ __noinline__ double proposal_score_literal(double theta, double mu, d
 // every group at once.  lcovar = log(covar).
 template <int K>
 __device__ __forceinline__ void proposal_scores(const Derived &cur, double alpha, const Derived &nw, double alphaN,
-                                                double sigma, double covar, double lcovar, int gb, int mi,
-                                                double &ptoCS, double &ctoPS) {
+                                                double sigma, double covar, double lcovar, double tame_slg,
+                                                int gb, int mi, double &ptoCS, double &ctoPS) {
   constexpr int len = K - 1;
   const double t1 = cur.q - alphaN;
   const double t2 = nw.q - alpha;
@@ -293,7 +296,7 @@ __device__ __forceinline__ void proposal_scores(const Derived &cur, double alpha
   const double ep1 = group_add<len>(e1, gb, mi), ep2 = group_add<len>(e2, gb, mi);
   ptoCS = (lcovar - cur.slg) + ep1;
   ctoPS = (lcovar - nw.slg) + ep2;
-  const bool tame = cur.slg > kTameSlg && nw.slg > kTameSlg && ep1 > kTameExp && ep2 > kTameExp;
+  const bool tame = cur.slg > tame_slg && nw.slg > tame_slg && ep1 > kTameExp && ep2 > kTameExp;
   if (__any_sync(0xffffffffu, !tame)) {
     const double lit1 = proposal_score_literal<K>(cur.psi, alphaN, sigma, covar, gb);
     const double lit2 = proposal_score_literal<K>(nw.psi, alpha, sigma, covar, gb);
@@ -462,7 +465,7 @@ __device__ void run_chain(const ChainParamsT<ROUNDS> &P, const GeneDesc &d, int 
     alphaB = alpha + sd * z;
     nwB = derive<K>(alphaB, offset_k, hyper_m1_k, lg_sum, lg_each, gb, mi);
     // ---- proposal densities (miso.c:531-534, :97-122), see proposal_scores
-    proposal_scores<K>(cur, alpha, nwB, alphaB, sigma, covar, lcovar, gb, mi, scP, scC);     // ptoCS, ctoPS
+    proposal_scores<K>(cur, alpha, nwB, alphaB, sigma, covar, lcovar, P.tame_slg, gb, mi, scP, scC);     // ptoCS, ctoPS
   };
 
   // m == -1 is the start-up proposal, adopted unconditionally (miso.c:834), followed

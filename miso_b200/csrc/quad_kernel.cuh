@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) quad_kernel(const __grid_consta
       if (m >= 0) {
         // ---- proposal densities (miso.c:531-534, :97-122), see proposal_scores (chain_kernel.cuh)
         double scP, scC;                                   // ptoCS, ctoPS
-        proposal_scores<K>(cur, alpha, nw, alphaN, sigma, covar, lcovar, gb, mi, scP, scC);
+        proposal_scores<K>(cur, alpha, nw, alphaN, sigma, covar, lcovar, P.tame_slg, gb, mi, scP, scC);
         // ---- joint scores (miso.c:524-529) ------------------------------------------------
         double rp;
         if (!paired) rp = count_dot<K>(cnt_k, rs_se_k, gb, mi);       // sum_r isoscores[ass_r], miso.c:267-271

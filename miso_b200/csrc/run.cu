@@ -598,6 +598,7 @@ static int prepare_bucket(Plan &plan, DevState *st, Launch *out) {
   P.n_ptab = n_ptab;
   P.ptab_min = 1.0;
   for (double v : plan.ptab) if (v > 0 && v < P.ptab_min) P.ptab_min = v;
+  P.tame_slg = std::getenv("MISOB200_LITERAL_SCORES") ? 1.0 : kTameSlg;      // (switch: tests of the literal route)
   P.samples = st->d_samples;
   P.loglik = st->d_loglik;
   P.samples_host = st->zc_samples;
@@ -678,6 +679,7 @@ static int prepare_quad(Plan &plan, DevState *st, Launch *out, int *rc) {
   P.n_ptab = (int) st->h_ptab.size();
   P.ptab_min = 1.0;
   for (double v : plan.ptab) if (v > 0 && v < P.ptab_min) P.ptab_min = v;
+  P.tame_slg = std::getenv("MISOB200_LITERAL_SCORES") ? 1.0 : kTameSlg;      // (switch: tests of the literal route)
   P.samples = st->d_samples;
   P.loglik = st->d_loglik;
   P.samples_host = st->zc_samples;

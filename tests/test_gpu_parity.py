@@ -238,3 +238,24 @@ def test_read_score_lookup_checked_and_unchecked(mb, port, monkeypatch):
     for g in range(16):
         want = oracle_gene(port, w.gene(g), True, params, gene_id=g)
         assert_gene_parity(plan.gene_result(out, g), want, tag="checked lookup gene %d" % g)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_literal_proposal_scores(mb, port, kind, chains_per_warp, monkeypatch):
+    """The proposal densities are evaluated in log space (proposal_scores, chain_kernel.cuh); the
+    reference's literal operation sequence (mvplogisnorm, miso.c:97-122) is kept for values a chain
+    does not normally see (a psi of 0, NaN, underflow).  MISOB200_LITERAL_SCORES=1 sends EVERY proposal
+    down that route: the same decisions as the oracle, and as the log-space route."""
+    w = mb.Workload(kind, 20, 300, 36, 250.0, 900.0, 4.0, seed=13, first_gene_id=40)
+    plan = mb.Plan().append(w)
+    params = mb.make_params(n_iters=500, burn_in=100, lag=5, n_chains=2, seed=5)
+    fast = plan.run(params)
+    fast = {k: np.array(v, copy=True) for k, v in fast.items() if isinstance(v, np.ndarray)}
+    monkeypatch.setenv("MISOB200_LITERAL_SCORES", "1")
+    lit = plan.run(params)
+    for g in range(20):
+        want = oracle_gene(port, w.gene(g), kind == 1, params, gene_id=40 + g)
+        assert_gene_parity(plan.gene_result(lit, g), want, tag="literal route, kind %d gene %d" % (kind, g))
+    np.testing.assert_array_equal(lit["assignment"], fast["assignment"])
+    np.testing.assert_array_equal(lit["rundata"], fast["rundata"])
+    np.testing.assert_allclose(lit["samples"], fast["samples"], rtol=1e-9, atol=0)
