@@ -5,8 +5,10 @@ The caller of the hot path in the reference is ``misopy/run_miso.py:34-202``
 its span, pair / strand-filter them (``misopy/sam_utils.py:210-456``), call
 ``MISOSampler.run_sampler`` once per gene.  That module is Python 2 and needs
 ``pysam``; this one restates the same steps for what this image can read --
-**GFF3 text and SAM text** -- and, instead of one sampler call per gene, puts all
-genes of the call into ONE plan, so the device sees a batch.
+**GFF3 text, and SAM text or BAM (+ BAI) alignments** (``miso_b200/bam.py``: BGZF, BAM
+records and the BAI index read directly, no pysam) -- and, instead of one sampler call
+per gene, puts all genes of the call into ONE plan, so the device sees a batch
+(SURVEY.md section 8f-4).
 
 Mirrored rules (file:line of the reference):
   * gene construction from gene -> mRNA/transcript -> exon records, transcripts in
@@ -37,6 +39,7 @@ from collections import OrderedDict, namedtuple
 import numpy as np
 
 from . import batch as _batch
+from .bam import BamFile, SamRead
 from .miso_format import format_header, write_miso
 from .sampler import GeneModel, Part
 
@@ -44,7 +47,6 @@ DEFAULT_SETTINGS = dict(num_iters=5000, burn_in=500, lag=10, num_chains=6, min_e
                         filter_reads=True, strand_rule="fr-unstranded")
 
 GffRecord = namedtuple("GffRecord", "seqid source type start end strand id parent")
-SamRead = namedtuple("SamRead", "qname flag rname pos cigar rlen aend")     # pos, aend 0-based, aend exclusive
 
 
 # ---- GFF3 ---------------------------------------------------------------------------------
@@ -144,11 +146,29 @@ def load_sam(path):
     return by_ref
 
 
+def load_alignments(path):
+    """``sam_utils.load_bam_reads`` (``sam_utils.py:143-152``): a BAM file (by its magic bytes; indexed
+    when ``<path>.bai`` exists) or SAM text."""
+    with open(path, "rb") as f:
+        magic = f.read(4)
+    if magic[:2] == b"\x1f\x8b":
+        return BamFile(path)
+    return load_sam(path)
+
+
 def fetch_reads_in_gene(sam, chrom, start, end):
-    """``sam_utils.py:155-181``: region fetch with the ``chr`` prefix fallback."""
-    if chrom not in sam:
+    """``sam_utils.py:155-181``: region fetch with the ``chr`` prefix fallback.  ``sam``: what
+    ``load_sam`` or ``load_alignments`` returned."""
+    names = sam.references if isinstance(sam, BamFile) else sam
+    if chrom not in names:
         parts = chrom.split("chr")
         chrom = parts[0] if len(parts) <= 1 else parts[1]
+    if isinstance(sam, BamFile):
+        try:
+            reads = sam.fetch(chrom, start, end)
+        except ValueError:                      # "Cannot fetch reads in region" (sam_utils.py:171-174)
+            reads = []
+        return [r for r in reads if not (r.flag & 4)]
     return [r for r in sam.get(chrom, ()) if r.pos < end and r.aend > start and not (r.flag & 4)]
 
 
@@ -245,7 +265,7 @@ def compute_gene_psi(gene_ids, gff_filename, sam_filename, output_dir, read_len,
     st = dict(DEFAULT_SETTINGS)
     st.update(settings or {})
     genes = load_gff_genes(gff_filename)
-    sam = load_sam(sam_filename)
+    sam = load_alignments(sam_filename)
     os.makedirs(output_dir, exist_ok=True)
     result, todo = OrderedDict(), []
     for gid in gene_ids:
@@ -324,10 +344,11 @@ def compute_gene_psi(gene_ids, gff_filename, sam_filename, output_dir, read_len,
 def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(
-        description="MISO on the B200: GFF3 + SAM -> .miso files (miso --run), .miso_summary "
+        description="MISO on the B200: GFF3 + SAM / BAM -> .miso files (miso --run), .miso_summary "
                     "(summarize_miso --summarize-samples), .miso_bf (compare_miso --compare-samples)")
-    ap.add_argument("--compute-gene-psi", nargs=4, metavar=("GENE_IDS", "GFF", "SAM", "OUTPUT_DIR"),
-                    help="comma-separated gene ids (or 'all'), GFF3 annotation, SAM alignments, output directory")
+    ap.add_argument("--compute-gene-psi", nargs=4, metavar=("GENE_IDS", "GFF", "ALIGNMENTS", "OUTPUT_DIR"),
+                    help="comma-separated gene ids (or 'all'), GFF3 annotation, SAM text or BAM (+ .bai) alignments, "
+                         "output directory")
     ap.add_argument("--summarize-samples", nargs=2, metavar=("SAMPLES_DIR", "OUTPUT_DIR"),
                     help="write OUTPUT_DIR/summary/<name of SAMPLES_DIR>.miso_summary (summarize_miso.py:24-47)")
     ap.add_argument("--compare-samples", nargs=3, metavar=("SAMPLES_DIR_1", "SAMPLES_DIR_2", "OUTPUT_DIR"),
