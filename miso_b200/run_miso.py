@@ -27,7 +27,8 @@ Mirrored rules (file:line of the reference):
     ``run_sampler`` (no reads, one isoform, output exists, every read unassignable,
     ``miso_sampler.py:229-277,352-354``)
   * defaults of ``misopy/settings/miso_settings.txt``: 5000 iterations, burn-in 500,
-    lag 10, 6 chains, at least 20 reads per event
+    lag 10, 6 chains, at least 20 reads per event; ``load_settings`` reads such a file
+    (``misopy/settings.py:19-145``)
   * output ``<output_dir>/<chrom>/<gene id>.miso`` in the format of
     ``miso_sampler.py:376-466`` (``miso_b200/miso_format.py``)
 Pairs are passed in order of first appearance of the read name (the reference iterates a
@@ -47,6 +48,47 @@ DEFAULT_SETTINGS = dict(num_iters=5000, burn_in=500, lag=10, num_chains=6, min_e
                         filter_reads=True, strand_rule="fr-unstranded")
 
 GffRecord = namedtuple("GffRecord", "seqid source type start end strand id parent")
+
+
+# ---- settings file ------------------------------------------------------------------------
+def _try_eval(text):
+    """``parse_csv.tryEval`` (``misopy/parse_csv.py:88-92``) without ``eval``: a Python literal, else the string."""
+    import ast
+    try:
+        return ast.literal_eval(text)
+    except (ValueError, SyntaxError):
+        return text
+
+
+def load_settings(path):
+    """A MISO settings file (``misopy/settings/miso_settings.txt``) as the ``settings`` dict of
+    ``compute_gene_psi``.  ``misopy/settings.py:19-60``: ConfigParser format, section headers ignored,
+    values evaluated as literals except in ``[cluster]``.  What the path reads (``run_miso.py:68-97``,
+    ``settings.py:62-145``): ``burn_in``, ``lag``, ``num_iters`` (required), ``num_chains`` (default 6),
+    ``min_event_reads`` (default 20), ``strand`` (default fr-unstranded, validated), ``filter_reads``
+    (default True).  ``num_processors`` and the cluster options have no meaning here (one batch on the GPU)."""
+    import configparser
+    if not os.path.isfile(path):
+        raise FileNotFoundError("Error: Settings file %s does not exist." % path)
+    cfg = configparser.ConfigParser()
+    cfg.read(path)
+    raw = {}
+    for section in cfg.sections():
+        for option in cfg.options(section):
+            v = cfg.get(section, option)
+            raw[option] = str(v) if section == "cluster" else _try_eval(v)
+    for name in ("burn_in", "lag", "num_iters"):
+        if name not in raw:
+            raise ValueError("Error: need %s parameter to be set in settings file." % name)
+    st = dict(DEFAULT_SETTINGS)
+    for name in ("burn_in", "lag", "num_iters", "num_chains", "min_event_reads", "filter_reads"):
+        if name in raw:
+            st[name] = raw[name]
+    if "strand" in raw:
+        if raw["strand"] not in ("fr-unstranded", "fr-firststrand", "fr-secondstrand"):
+            raise ValueError("Error: Invalid strand parameter %s" % raw["strand"])
+        st["strand_rule"] = raw["strand"]
+    return st
 
 
 # ---- GFF3 ---------------------------------------------------------------------------------
@@ -357,6 +399,8 @@ def main(argv=None):
     ap.add_argument("--overhang-len", type=int, default=1)
     ap.add_argument("--paired-end", nargs=2, type=float, metavar=("MEAN", "SD"), default=None)
     ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--settings-filename", default=None,
+                    help="MISO settings file (misopy/settings/miso_settings.txt format); default: its shipped values")
     a = ap.parse_args(argv)
     if a.summarize_samples:
         from .postprocess import summarize_sampler_results
@@ -373,8 +417,9 @@ def main(argv=None):
             ap.error("--compute-gene-psi needs --read-len")
         ids, gff, sam, out = a.compute_gene_psi
         gene_ids = list(load_gff_genes(gff)) if ids == "all" else ids.split(",")
-        res = compute_gene_psi(gene_ids, gff, sam, out, a.read_len, a.overhang_len, a.paired_end, seed=a.seed,
-                               verbose=True)
+        res = compute_gene_psi(gene_ids, gff, sam, out, a.read_len, a.overhang_len, a.paired_end,
+                               settings=load_settings(a.settings_filename) if a.settings_filename else None,
+                               seed=a.seed, verbose=True)
         for gid, r in res.items():
             print("%s\t%s" % (gid, r))
     else:

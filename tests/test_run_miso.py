@@ -163,3 +163,27 @@ def test_exons_without_id_and_shared_labels():
     g = GeneModel("g", parts, [["a", "b", "c"], ["a", "c"]])
     assert [len(i.parts) for i in g.isoforms] == [3, 2]
     assert [p.label for p in g.isoforms[1].parts] == ["a", "c"]
+
+
+def test_settings_file(tmp_path):
+    """misopy/settings.py: ConfigParser file, sections ignored, literals evaluated, defaults and checks of
+    get_sampler_params / get_min_event_reads / get_strand_param."""
+    from miso_b200 import run_miso as rm
+    ref = "/root/reference/misopy/settings/miso_settings.txt"
+    if os.path.isfile(ref):
+        st = rm.load_settings(ref)
+        assert st == dict(rm.DEFAULT_SETTINGS)          # the shipped file IS the defaults
+    p = tmp_path / "s.txt"
+    p.write_text("[data]\nfilter_results = True\nmin_event_reads = 5\nstrand = fr-firststrand\n"
+                 "[cluster]\ncluster_command = long\n[sampler]\nburn_in = 100\nlag = 2\nnum_iters = 1000\n")
+    st = rm.load_settings(str(p))
+    assert (st["burn_in"], st["lag"], st["num_iters"], st["num_chains"]) == (100, 2, 1000, 6)
+    assert st["min_event_reads"] == 5 and st["strand_rule"] == "fr-firststrand" and st["filter_reads"] is True
+    p.write_text("[sampler]\nburn_in = 100\nlag = 2\n")
+    with pytest.raises(ValueError, match="num_iters"):
+        rm.load_settings(str(p))
+    p.write_text("[data]\nstrand = sideways\n[sampler]\nburn_in = 1\nlag = 1\nnum_iters = 10\n")
+    with pytest.raises(ValueError, match="Invalid strand"):
+        rm.load_settings(str(p))
+    with pytest.raises(FileNotFoundError):
+        rm.load_settings(str(tmp_path / "missing.txt"))
