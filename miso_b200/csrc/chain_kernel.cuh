@@ -14,17 +14,20 @@
 //                    lane-distributed: lane k holds alpha_k, psi_k, the
 //                    normalised log psi_k, prior and length terms of isoform k;
 //                    Philox counters/keys; per-lane assignment counts.
-//   warp shuffles  : the K-wide serial sums / max of the reference
-//                    (score_iso, ldirichlet, logit_inv, mvplogisnorm) are done
-//                    in the reference's order by broadcasting lane i's term.
+//   warp shuffles  : the K-wide sums / max of the reference (score_iso,
+//                    ldirichlet, logit_inv, mvplogisnorm) are reductions inside
+//                    a group of eight lanes (group_reduce: gather or xor fold).
 //   tensor cores   : unused on purpose -- no dense contraction on this path.
 //
 // Decision parity: every compare the reference makes in fp64
-// (rand*sumpsi vs cumsum, U vs acceptP) is made here with the same operands
-// in the same operation order (this file is compiled with -fmad=false so a
-// multiply feeding an add is not contracted).  The MH ratio uses per-isoform
-// assignment counts (sum_k n_k * logpsi_k) instead of a serial sum over reads:
-// same value up to fp64 rounding, see DESIGN.md "parity contract".
+// (rand*sumpsi vs cumsum, U vs acceptP) is made here on operands that equal the
+// reference's up to fp64 rounding (this file is compiled with -fmad=false so a
+// multiply feeding an add is not contracted; the thresholds of the read pass carry
+// their own exactness argument, class_pass.cuh).  Three things are not the reference's
+// operation sequence, each the same value up to rounding: the MH ratio uses
+// per-isoform assignment counts (sum_k n_k * logpsi_k) instead of a serial sum over
+// reads, the K-wide sums are not added left to right, and the proposal densities
+// are evaluated in log space (proposal_scores).  See DESIGN.md "parity contract".
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
