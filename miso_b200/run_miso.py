@@ -310,31 +310,35 @@ def compute_gene_psi(gene_ids, gff_filename, sam_filename, output_dir, read_len,
     sam = load_alignments(sam_filename)
     os.makedirs(output_dir, exist_ok=True)
     result, todo = OrderedDict(), []
-    for gid in gene_ids:
-        if gid not in genes:
-            result[gid] = "skipped: not in the GFF"
-            continue
-        gene = make_gene_from_gff_records(gid, genes[gid])
-        iso_lens = [sum(p.end - p.start + 1 for p in iso.parts) for iso in gene.isoforms]
-        if all(l < read_len for l in iso_lens):                                   # run_miso.py:110-113
-            result[gid] = "skipped: all isoforms shorter than the read"
-            continue
-        tx_start, tx_end = get_inclusive_txn_bounds(genes[gid])
-        raw = fetch_reads_in_gene(sam, gene.chrom, tx_start, tx_end)
-        reads, n_raw = sam_parse_reads(raw, paired_end=bool(paired_end), strand_rule=st["strand_rule"],
-                                       target_strand=gene.strand, given_read_len=read_len)
-        if st["filter_reads"] and n_raw < st["min_event_reads"]:                  # run_miso.py:134-141
-            result[gid] = "skipped: only %d reads in gene (needed >= %d)" % (n_raw, st["min_event_reads"])
-            continue
-        out_file = os.path.join(output_dir, gene.chrom, gid) + ".miso"
-        if len(reads[0]) == 0:                                                    # miso_sampler.py:229-231
-            result[gid] = "skipped: no reads"
-        elif os.path.isfile(os.path.normpath(out_file)):                          # :233-238
-            result[gid] = "skipped: output exists"
-        elif len(gene.isoforms) == 1:                                             # :272-277
-            result[gid] = "skipped: one isoform"
-        else:
-            todo.append((gid, gene, reads, out_file))
+    try:
+        for gid in gene_ids:
+            if gid not in genes:
+                result[gid] = "skipped: not in the GFF"
+                continue
+            gene = make_gene_from_gff_records(gid, genes[gid])
+            iso_lens = [sum(p.end - p.start + 1 for p in iso.parts) for iso in gene.isoforms]
+            if all(l < read_len for l in iso_lens):                                   # run_miso.py:110-113
+                result[gid] = "skipped: all isoforms shorter than the read"
+                continue
+            tx_start, tx_end = get_inclusive_txn_bounds(genes[gid])
+            raw = fetch_reads_in_gene(sam, gene.chrom, tx_start, tx_end)
+            reads, n_raw = sam_parse_reads(raw, paired_end=bool(paired_end), strand_rule=st["strand_rule"],
+                                           target_strand=gene.strand, given_read_len=read_len)
+            if st["filter_reads"] and n_raw < st["min_event_reads"]:                  # run_miso.py:134-141
+                result[gid] = "skipped: only %d reads in gene (needed >= %d)" % (n_raw, st["min_event_reads"])
+                continue
+            out_file = os.path.join(output_dir, gene.chrom, gid) + ".miso"
+            if len(reads[0]) == 0:                                                    # miso_sampler.py:229-231
+                result[gid] = "skipped: no reads"
+            elif os.path.isfile(os.path.normpath(out_file)):                          # :233-238
+                result[gid] = "skipped: output exists"
+            elif len(gene.isoforms) == 1:                                             # :272-277
+                result[gid] = "skipped: one isoform"
+            else:
+                todo.append((gid, gene, reads, out_file))
+    finally:
+        if isinstance(sam, BamFile):
+            sam.close()
     if not todo:
         return result
 
