@@ -171,7 +171,7 @@ namespace misob200 {
 // consume the groups in order; the first accept throws the rest of the batch away.
 // With the 20-40 % acceptance of K >= 3 chains a batch serves ~2.5 iterations for the
 // instruction count of one.  Nothing about the arithmetic changes: every group runs
-// the reference's operations in the reference's order on its own operands.
+// the same operations on its own operands, whichever group ends up being consumed.
 constexpr int kSpec = 4;
 
 // Everything derived from a candidate alpha (member i < K-1 of a group holds alpha_i).
