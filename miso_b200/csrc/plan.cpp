@@ -461,19 +461,40 @@ static int build_and_merge(Plan &plan, const misob200_reads_t &in, int n_threads
     for (auto &t : pool) t.join();
   }
   auto t_merge = std::chrono::steady_clock::now();
+  // merge: offsets in gene order (serial, a few words per gene), then the tile bytes copied into the
+  // arena by the worker threads -- one growth of the arena per append instead of one per gene
+  size_t tile_at = plan.tiles.size();
+  plan.desc.reserve(plan.desc.size() + (size_t) G);
+  plan.host.reserve(plan.host.size() + (size_t) G);
   for (int g = 0; g < G; g++) {
     GeneOut &o = outs[g];
     o.h.read_base = plan.n_reads;
     o.d.status = o.h.status;
-    o.d.tile_off = plan.tiles.size();
+    o.d.tile_off = tile_at;
     o.d.drawn_off = plan.n_drawn;
-    plan.tiles.insert(plan.tiles.end(), o.tile.begin(), o.tile.end());
+    tile_at += o.tile.size();
     plan.n_reads += o.h.R;
     plan.n_drawn += (o.h.R2 + 15) / 16 * 16;
     plan.desc.push_back(o.d);
-    plan.host.push_back(std::move(o.h));
-    std::vector<uint8_t>().swap(o.tile);
   }
+  plan.tiles.resize(tile_at);
+  const size_t first_desc = plan.desc.size() - (size_t) G;
+  std::atomic<int> next_copy(0);
+  auto copy = [&]() {
+    for (int g0; (g0 = next_copy.fetch_add(256)) < G;)
+      for (int g = g0; g < std::min(G, g0 + 256); g++) {
+        GeneOut &o = outs[g];
+        if (!o.tile.empty()) std::memcpy(plan.tiles.data() + plan.desc[first_desc + g].tile_off, o.tile.data(), o.tile.size());
+        std::vector<uint8_t>().swap(o.tile);
+      }
+  };
+  if (nt == 1 || G < 1024) copy();
+  else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; t++) pool.emplace_back(copy);
+    for (auto &t : pool) t.join();
+  }
+  for (int g = 0; g < G; g++) plan.host.push_back(std::move(outs[g].h));
   if (std::getenv("MISOB200_PLAN_PROFILE")) {
     const double merge = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_merge).count();
     fprintf(stderr, "[plan profile] thread-seconds: match %.3f sort %.3f classes %.3f consts+split %.3f weight classes %.3f tile %.3f; merge (serial) %.3f s\n",
