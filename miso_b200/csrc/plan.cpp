@@ -122,14 +122,30 @@ void build_gene(const Plan &plan, const misob200_reads_t &in, int g, GeneOut &ou
   } else {
   for (int r = 0; r < R; r++) order[r] = r;
   if ((int) plan.code_rank.size() == n_codes && !std::getenv("MISOB200_SORT_DOUBLES")) {
-    std::vector<unsigned __int128> key(R > 0 ? R : 1);
-    for (int r = 0; r < R; r++) {
-      unsigned __int128 v = 0;
-      for (int k = 0; k < K; k++) v = (v << 16) | plan.code_rank[codes[(size_t) r * K + k]];
-      key[r] = v;
+    // one integer key per read: the ranks of its K probabilities, isoform 0 most significant.  The
+    // comparison only sees the order of the keys, so the narrowest field that holds every rank does
+    // (8 bits for the usual <= 256 distinct fragment-length probabilities: a 64-bit key for any K)
+    int max_rank = 0;                      // (dense ranks: the largest is the last distinct value's)
+    for (uint16_t v : plan.code_rank) max_rank = std::max<int>(max_rank, v);
+    if (max_rank < 256) {
+      std::vector<uint64_t> key(R > 0 ? R : 1);
+      for (int r = 0; r < R; r++) {
+        uint64_t v = 0;
+        for (int k = 0; k < K; k++) v = (v << 8) | plan.code_rank[codes[(size_t) r * K + k]];
+        key[r] = v;
+      }
+      BMSort<KeyCmp<uint64_t>> sorter{KeyCmp<uint64_t>{key.data()}};
+      sorter.sort(order.data(), R);
+    } else {
+      std::vector<unsigned __int128> key(R > 0 ? R : 1);
+      for (int r = 0; r < R; r++) {
+        unsigned __int128 v = 0;
+        for (int k = 0; k < K; k++) v = (v << 16) | plan.code_rank[codes[(size_t) r * K + k]];
+        key[r] = v;
+      }
+      BMSort<KeyCmp<unsigned __int128>> sorter{KeyCmp<unsigned __int128>{key.data()}};
+      sorter.sort(order.data(), R);
     }
-    BMSort<KeyCmp<unsigned __int128>> sorter{KeyCmp<unsigned __int128>{key.data()}};
-    sorter.sort(order.data(), R);
   } else {
     BMSort<ColCmp> sorter{ColCmp{codes.data(), plan.ptab.data(), K}};
     sorter.sort(order.data(), R);
